@@ -1,0 +1,432 @@
+// posefit_math.h -- per-object 3x3 arithmetic of the pose solver, shared by the CUDA kernels
+// (posefit_kernels.cu) and by a host-compiled checker (tests/host/math_check.cpp).
+//
+// What it implements (reference: PoseEst/pose_utils.py of the upstream repo):
+//   * the Umeyama/Procrustes solve of estimateSimilarityUmeyama (pose_utils.py:16-61) from
+//     accumulated moments instead of centred point arrays;
+//   * the total residual of evaluateModel (pose_utils.py:5-9) in closed form from the global
+//     second moments, so RANSAC hypotheses are ranked without a per-point pass;
+//   * the adjoint of the fit (no reference exists: the upstream code detaches before the
+//     fit, Detection/tracker/postprocess.py:151).
+//
+// The rotation is NOT taken from a LAPACK-style SVD.  R = U S V^T with S = diag(1,1,det(U)det(V))
+// (pose_utils.py:38-44) is the maximiser of tr(R^T C) over SO(3); we get a start from a
+// one-sided (Hestenes) Jacobi sweep in registers and polish it with Newton steps on SO(3),
+// which also yields H = R^T C and L = tr(H) I - H -- everything the scale and the backward
+// pass need -- without ever forming U, V or the singular values.
+#pragma once
+
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define PF_HD __host__ __device__ __forceinline__
+#else
+#define PF_HD inline
+#endif
+
+namespace posefit {
+
+// ---------------------------------------------------------------------------------------------
+// small helpers
+// ---------------------------------------------------------------------------------------------
+PF_HD float pf_rsqrt(float x) {
+#if defined(__CUDA_ARCH__)
+  return rsqrtf(x);
+#else
+  return 1.0f / sqrtf(x);
+#endif
+}
+PF_HD double pf_rsqrt(double x) {
+#if defined(__CUDA_ARCH__)
+  return rsqrt(x);
+#else
+  return 1.0 / sqrt(x);
+#endif
+}
+PF_HD float pf_abs(float x) { return fabsf(x); }
+PF_HD double pf_abs(double x) { return fabs(x); }
+PF_HD float pf_sqrt(float x) { return sqrtf(x); }
+PF_HD double pf_sqrt(double x) { return sqrt(x); }
+
+template <typename T>
+PF_HD void cross3(const T* a, const T* b, T* c) {
+  c[0] = a[1] * b[2] - a[2] * b[1];
+  c[1] = a[2] * b[0] - a[0] * b[2];
+  c[2] = a[0] * b[1] - a[1] * b[0];
+}
+
+// ---------------------------------------------------------------------------------------------
+// One-sided Jacobi on a 3x3 matrix held as three columns: on exit the columns of `a` are
+// mutually orthogonal (a = A V), `v` holds V.  High relative accuracy for small singular
+// values, which a Jacobi on A^T A would lose.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+PF_HD void jacobi_pair(T* ap, T* aq, T* vp, T* vq) {
+  const T alpha = ap[0] * ap[0] + ap[1] * ap[1] + ap[2] * ap[2];
+  const T beta = aq[0] * aq[0] + aq[1] * aq[1] + aq[2] * aq[2];
+  const T gamma = ap[0] * aq[0] + ap[1] * aq[1] + ap[2] * aq[2];
+  const T eps = sizeof(T) == 4 ? (T)1e-14 : (T)1e-30;      // (relative tolerance)^2
+  if (!(gamma * gamma > eps * alpha * beta)) return;        // already orthogonal (or NaN / zero)
+  const T zeta = (beta - alpha) / ((T)2 * gamma);
+  const T tt = (zeta >= (T)0 ? (T)1 : (T)-1) / (pf_abs(zeta) + pf_sqrt((T)1 + zeta * zeta));
+  const T c = pf_rsqrt((T)1 + tt * tt);
+  const T s = c * tt;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const T x = ap[i], y = aq[i];
+    ap[i] = c * x - s * y;
+    aq[i] = s * x + c * y;
+    const T vx = vp[i], vy = vq[i];
+    vp[i] = c * vx - s * vy;
+    vq[i] = s * vx + c * vy;
+  }
+}
+
+template <typename T>
+PF_HD void swap_cols(T* a, T* b) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i) { const T t = a[i]; a[i] = b[i]; b[i] = t; }
+}
+
+// Start rotation from the covariance C (row-major 3x3, any scale).  Returns false when C == 0
+// (numpy's SVD of the zero matrix gives U = Vh = I, so the reference rotation is I).
+template <typename T, int SWEEPS>
+PF_HD bool rotation_start(const double* C, double* R) {
+  double m = 0.0;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) m = fmax(m, fabs(C[i]));
+  if (!(m > 0.0) || !(m < 1e300)) {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) R[i] = (i % 4 == 0) ? 1.0 : 0.0;
+    return false;
+  }
+  const double inv = 1.0 / m;
+  T a0[3], a1[3], a2[3], v0[3] = {1, 0, 0}, v1[3] = {0, 1, 0}, v2[3] = {0, 0, 1};
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    a0[i] = (T)(C[3 * i + 0] * inv);
+    a1[i] = (T)(C[3 * i + 1] * inv);
+    a2[i] = (T)(C[3 * i + 2] * inv);
+  }
+#pragma unroll 1
+  for (int sweep = 0; sweep < SWEEPS; ++sweep) {
+    jacobi_pair(a0, a1, v0, v1);
+    jacobi_pair(a0, a2, v0, v2);
+    jacobi_pair(a1, a2, v1, v2);
+  }
+  T n0 = a0[0] * a0[0] + a0[1] * a0[1] + a0[2] * a0[2];
+  T n1 = a1[0] * a1[0] + a1[1] * a1[1] + a1[2] * a1[2];
+  T n2 = a2[0] * a2[0] + a2[1] * a2[1] + a2[2] * a2[2];
+  // bring the two largest singular directions to slots 0 and 1
+  if (n0 < n1) { swap_cols(a0, a1); swap_cols(v0, v1); const T t = n0; n0 = n1; n1 = t; }
+  if (n0 < n2) { swap_cols(a0, a2); swap_cols(v0, v2); const T t = n0; n0 = n2; n2 = t; }
+  if (n1 < n2) { swap_cols(a1, a2); swap_cols(v1, v2); const T t = n1; n1 = n2; n2 = t; }
+  T u0[3], u1[3], u2[3], w2[3];
+  const T r0 = pf_rsqrt(n0);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) u0[i] = a0[i] * r0;
+  T d = u0[0] * a1[0] + u0[1] * a1[1] + u0[2] * a1[2];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) u1[i] = a1[i] - d * u0[i];
+  T l1 = u1[0] * u1[0] + u1[1] * u1[1] + u1[2] * u1[2];
+  const T tiny = sizeof(T) == 4 ? (T)1e-12 : (T)1e-28;
+  if (!(l1 > tiny)) {                       // rank one: any unit vector orthogonal to u0 will do
+    const T x = pf_abs(u0[0]), y = pf_abs(u0[1]), z = pf_abs(u0[2]);
+    T e[3] = {0, 0, 0};
+    if (x <= y && x <= z) e[0] = 1; else if (y <= z) e[1] = 1; else e[2] = 1;
+    d = u0[0] * e[0] + u0[1] * e[1] + u0[2] * e[2];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) u1[i] = e[i] - d * u0[i];
+    l1 = u1[0] * u1[0] + u1[1] * u1[1] + u1[2] * u1[2];
+  }
+  const T r1 = pf_rsqrt(l1);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) u1[i] *= r1;
+  cross3(u0, u1, u2);
+  cross3(v0, v1, w2);                       // det(+1) on both sides == the reflection fix of :39-42
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      R[3 * i + j] = (double)u0[i] * (double)v0[j] + (double)u1[i] * (double)v1[j] + (double)u2[i] * (double)w2[j];
+  return true;
+}
+
+// R <- R (1.5 I - 0.5 R^T R): one Newton-Schulz step towards the nearest orthogonal matrix.
+PF_HD void orthonormalize_step(double* R) {
+  double G[9];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      G[3 * i + j] = -0.5 * (R[i] * R[j] + R[3 + i] * R[3 + j] + R[6 + i] * R[6 + j]) + (i == j ? 1.5 : 0.0);
+  double N[9];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      N[3 * i + j] = R[3 * i] * G[j] + R[3 * i + 1] * G[3 + j] + R[3 * i + 2] * G[6 + j];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) R[i] = N[i];
+}
+
+// M = R^T C
+PF_HD void rt_times(const double* R, const double* C, double* M) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      M[3 * i + j] = R[i] * C[j] + R[3 + i] * C[3 + j] + R[6 + i] * C[6 + j];
+}
+
+// inverse of the symmetric 3x3 L = tr(H) I - H given H = (h00,h01,h02,h11,h12,h22).
+// Returns det(L); Li is only written when |det| is usable.
+PF_HD double inv_trace_minus(const double* H, double* Li) {
+  const double tr = H[0] + H[3] + H[5];
+  const double l00 = tr - H[0], l11 = tr - H[3], l22 = tr - H[5];
+  const double l01 = -H[1], l02 = -H[2], l12 = -H[4];
+  const double c00 = l11 * l22 - l12 * l12;
+  const double c01 = l02 * l12 - l01 * l22;
+  const double c02 = l01 * l12 - l02 * l11;
+  const double det = l00 * c00 + l01 * c01 + l02 * c02;
+  if (fabs(det) > 1e-200 && fabs(det) < 1e200) {
+    const double r = 1.0 / det;
+    Li[0] = c00 * r; Li[1] = c01 * r; Li[2] = c02 * r;
+    Li[3] = (l00 * l22 - l02 * l02) * r;
+    Li[4] = (l01 * l02 - l00 * l12) * r;
+    Li[5] = (l00 * l11 - l01 * l01) * r;
+  }
+  return det;
+}
+
+// One Newton step on SO(3) towards skew(R^T C) = 0.  Returns |k|_inf (the skew residual before
+// the step) so callers can test convergence.
+PF_HD double newton_step(const double* C, double* R) {
+  double M[9];
+  rt_times(R, C, M);
+  const double H[6] = {M[0], 0.5 * (M[1] + M[3]), 0.5 * (M[2] + M[6]), M[4], 0.5 * (M[5] + M[7]), M[8]};
+  const double k0 = M[7] - M[5], k1 = M[2] - M[6], k2 = M[3] - M[1];
+  double Li[6] = {0, 0, 0, 0, 0, 0};
+  const double det = inv_trace_minus(H, Li);
+  const double kn = fmax(fabs(k0), fmax(fabs(k1), fabs(k2)));
+  if (!(fabs(det) > 1e-200)) return kn;
+  double w0 = Li[0] * k0 + Li[1] * k1 + Li[2] * k2;
+  double w1 = Li[1] * k0 + Li[3] * k1 + Li[4] * k2;
+  double w2 = Li[2] * k0 + Li[4] * k1 + Li[5] * k2;
+  double th2 = w0 * w0 + w1 * w1 + w2 * w2;
+  if (!(th2 < 1e300)) return kn;
+  if (th2 > 0.25) {                           // damp wild steps (ill-conditioned start)
+    const double f = 0.5 * pf_rsqrt(th2);
+    w0 *= f; w1 *= f; w2 *= f; th2 = 0.25;
+  }
+  // Rodrigues with series coefficients (|w| <= 0.5): a = sin(t)/t, b = (1-cos t)/t^2
+  const double a = 1.0 - th2 * (1.0 / 6.0 - th2 * (1.0 / 120.0 - th2 * (1.0 / 5040.0 - th2 * (1.0 / 362880.0))));
+  const double b = 0.5 - th2 * (1.0 / 24.0 - th2 * (1.0 / 720.0 - th2 * (1.0 / 40320.0 - th2 * (1.0 / 3628800.0))));
+  // E = I + a [w]x + b [w]x^2,  [w]x^2 = w w^T - |w|^2 I
+  double E[9];
+  E[0] = 1.0 + b * (w0 * w0 - th2); E[1] = -a * w2 + b * w0 * w1;      E[2] = a * w1 + b * w0 * w2;
+  E[3] = a * w2 + b * w0 * w1;      E[4] = 1.0 + b * (w1 * w1 - th2); E[5] = -a * w0 + b * w1 * w2;
+  E[6] = -a * w1 + b * w0 * w2;     E[7] = a * w0 + b * w1 * w2;      E[8] = 1.0 + b * (w2 * w2 - th2);
+  double N[9];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      N[3 * i + j] = R[3 * i] * E[j] + R[3 * i + 1] * E[3 + j] + R[3 * i + 2] * E[6 + j];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) R[i] = N[i];
+  return kn;
+}
+
+// ---------------------------------------------------------------------------------------------
+// The fit.  Sums are UNcentred, over the points that take part (weights 0/1).
+// ---------------------------------------------------------------------------------------------
+struct Moments {
+  double n;        // number of points
+  double sx[3];    // sum x           (x = noc - 0.5, "source")
+  double sy[3];    // sum y           (y = back-projected depth point, "target")
+  double syx[9];   // sum y_i x_j     row-major [i][j]
+  double sxx;      // sum |x|^2
+};
+
+struct Fit {
+  double s;        // scale (Scales[0], pose_utils.py:47-52)
+  double R[9];     // TRUE rotation R = U S V^T; the reference reports its transpose (:44)
+  double t[3];     // Translation (:55)
+  double mux[3], muy[3];
+  double var;      // sum of per-axis population variances of x (:46)
+  double H[6];     // sym part of R^T C  (h00,h01,h02,h11,h12,h22)
+  double Linv[6];  // (tr(H) I - H)^-1, zero when singular
+  double n;
+  int status;      // 0 ok, 1 empty, 3 NaN covariance (:32-36)
+};
+
+enum { PF_OK = 0, PF_EMPTY = 1, PF_LOW_INLIER_RATIO = 2, PF_NAN = 3 };
+
+// Rotation maximising tr(R^T C) over SO(3) plus H and Linv.  PRECISE=true: double Jacobi start
+// (used once per object); false: float start + more Newton steps (used per RANSAC hypothesis),
+// falling back to the double start if the skew residual has not collapsed.
+template <bool PRECISE>
+PF_HD void solve_rotation(const double* C, double* R, double* H, double* Linv) {
+  double m = 0.0;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) m = fmax(m, fabs(C[i]));
+  bool nonzero;
+  if (PRECISE) nonzero = rotation_start<double, 6>(C, R);
+  else nonzero = rotation_start<float, 4>(C, R);
+#pragma unroll
+  for (int i = 0; i < 6; ++i) { H[i] = 0.0; Linv[i] = 0.0; }
+  if (!nonzero) return;
+  double Cn[9];
+  const double inv = 1.0 / m;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) Cn[i] = C[i] * inv;
+  if (!PRECISE) {
+    orthonormalize_step(R);
+    newton_step(Cn, R);
+    newton_step(Cn, R);
+    const double kn = newton_step(Cn, R);     // residual BEFORE the third step
+    if (!(kn < 1e-7)) {                       // not in the quadratic regime: redo from a double start
+      rotation_start<double, 6>(C, R);
+      newton_step(Cn, R);
+    }
+  }
+  newton_step(Cn, R);
+  orthonormalize_step(R);
+  double M[9];
+  rt_times(R, Cn, M);
+  double Hn[6] = {M[0], 0.5 * (M[1] + M[3]), 0.5 * (M[2] + M[6]), M[4], 0.5 * (M[5] + M[7]), M[8]};
+  double Li[6] = {0, 0, 0, 0, 0, 0};
+  inv_trace_minus(Hn, Li);
+#pragma unroll
+  for (int i = 0; i < 6; ++i) { H[i] = Hn[i] * m; Linv[i] = Li[i] * inv; }
+}
+
+template <bool PRECISE>
+PF_HD void fit_from_moments(const Moments& mo, Fit& f) {
+  f.n = mo.n;
+  f.s = 1.0;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) f.R[i] = (i % 4 == 0) ? 1.0 : 0.0;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) { f.t[i] = 0.0; f.mux[i] = 0.0; f.muy[i] = 0.0; }
+#pragma unroll
+  for (int i = 0; i < 6; ++i) { f.H[i] = 0.0; f.Linv[i] = 0.0; }
+  f.var = 0.0;
+  if (!(mo.n > 0.0)) { f.status = PF_EMPTY; return; }
+  const double rn = 1.0 / mo.n;
+  double C[9];
+  bool nan = false;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) { f.mux[i] = mo.sx[i] * rn; f.muy[i] = mo.sy[i] * rn; }
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      C[3 * i + j] = mo.syx[3 * i + j] * rn - f.muy[i] * f.mux[j];
+      nan = nan || (C[3 * i + j] != C[3 * i + j]);
+    }
+  if (nan) { f.status = PF_NAN; return; }
+  f.var = mo.sxx * rn - (f.mux[0] * f.mux[0] + f.mux[1] * f.mux[1] + f.mux[2] * f.mux[2]);
+  solve_rotation<PRECISE>(C, f.R, f.H, f.Linv);
+  const double trh = f.H[0] + f.H[3] + f.H[5];           // = sum(D) after the sign fix (:39-42)
+  f.s = (f.var * trh != 0.0) ? (1.0 / f.var) * trh : 1.0;   // pose_utils.py:47-50
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+    f.t[i] = f.muy[i] - f.s * (f.R[3 * i] * f.mux[0] + f.R[3 * i + 1] * f.mux[1] + f.R[3 * i + 2] * f.mux[2]);
+  f.status = PF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Closed-form total residual of evaluateModel (pose_utils.py:7-9) for the transform [A | t]:
+//   sum_i |y_i - A x_i - t|^2 = Syy - 2 <A, Syx> + <A Sxx, A> + n |mu_y - A mu_x - t|^2
+// with CENTRED global sums Syy = sum |y~|^2, Syx = sum y~ x~^T, Sxx = sum x~ x~^T.
+// ---------------------------------------------------------------------------------------------
+struct GlobalStats {
+  double n;
+  double mux[3], muy[3];
+  double Syy;
+  double Syx[9];
+  double Sxx[6];   // xx, xy, xz, yy, yz, zz
+};
+
+PF_HD double residual_sq(const GlobalStats& g, const double* A, const double* t) {
+  double acc = g.Syy;
+  double lin = 0.0;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) lin += A[i] * g.Syx[i];
+  acc -= 2.0 * lin;
+  const double X[9] = {g.Sxx[0], g.Sxx[1], g.Sxx[2], g.Sxx[1], g.Sxx[3], g.Sxx[4], g.Sxx[2], g.Sxx[4], g.Sxx[5]};
+  double quad = 0.0;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      quad += (A[3 * i] * X[j] + A[3 * i + 1] * X[3 + j] + A[3 * i + 2] * X[6 + j]) * A[3 * i + j];
+  acc += quad;
+  double dd = 0.0;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const double d = g.muy[i] - (A[3 * i] * g.mux[0] + A[3 * i + 1] * g.mux[1] + A[3 * i + 2] * g.mux[2]) - t[i];
+    dd += d * d;
+  }
+  return acc + g.n * dd;
+}
+
+// Scoring transform of a fit.  ref_compat: A = s * R^T, the block the reference really builds
+// (pose_utils.py:58); otherwise the geometrically correct A = s * R.
+PF_HD void scoring_transform(const Fit& f, bool ref_compat, double* A) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) A[3 * i + j] = f.s * (ref_compat ? f.R[3 * j + i] : f.R[3 * i + j]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Adjoint of the fit.  Given dL/ds, dL/dR (w.r.t. the TRUE rotation), dL/dt, produce the
+// per-point coefficients:  dL/dx_i = (w_i/n) (GC^T y~_i + 2 gvar x~_i + gmux),
+//                          dL/dy_i = (w_i/n) (GC x~_i + gmuy)
+// Rotation part: dR = R [dw]x with (tr(H) I - H) dw = axial(R^T dC - dC^T R)  =>  GC_rot = R [p]x,
+// p = Linv q, q = axial(R^T G_R) (same linear system as the forward Newton step).
+// ---------------------------------------------------------------------------------------------
+struct FitAdjoint {
+  double GC[9];
+  double gvar;
+  double gmux[3], gmuy[3];
+};
+
+PF_HD void fit_adjoint(const Fit& f, double gs, const double* gR, const double* gt, FitAdjoint& a) {
+  const bool scale_live = (f.var * (f.H[0] + f.H[3] + f.H[5]) != 0.0);
+  // t = muy - s R mux
+  double Rmu[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) Rmu[i] = f.R[3 * i] * f.mux[0] + f.R[3 * i + 1] * f.mux[1] + f.R[3 * i + 2] * f.mux[2];
+  double gs2 = gs - (gt[0] * Rmu[0] + gt[1] * Rmu[1] + gt[2] * Rmu[2]);
+  double G[9];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) G[3 * i + j] = gR[3 * i + j] - f.s * gt[i] * f.mux[j];
+  double Q[9];
+  rt_times(f.R, G, Q);                                    // Q = R^T G
+  const double q0 = Q[7] - Q[5], q1 = Q[2] - Q[6], q2 = Q[3] - Q[1];
+  const double p0 = f.Linv[0] * q0 + f.Linv[1] * q1 + f.Linv[2] * q2;
+  const double p1 = f.Linv[1] * q0 + f.Linv[3] * q1 + f.Linv[4] * q2;
+  const double p2 = f.Linv[2] * q0 + f.Linv[4] * q1 + f.Linv[5] * q2;
+  const double P[9] = {0.0, -p2, p1, p2, 0.0, -p0, -p1, p0, 0.0};
+  if (!scale_live) gs2 = 0.0;                             // s is the constant 1 (pose_utils.py:50)
+  const double ginv = (f.var != 0.0) ? gs2 / f.var : 0.0;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      a.GC[3 * i + j] = f.R[3 * i] * P[j] + f.R[3 * i + 1] * P[3 + j] + f.R[3 * i + 2] * P[6 + j] + ginv * f.R[3 * i + j];
+  a.gvar = -ginv * f.s;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    a.gmux[i] = -f.s * (f.R[i] * gt[0] + f.R[3 + i] * gt[1] + f.R[6 + i] * gt[2]);
+    a.gmuy[i] = gt[i];
+  }
+}
+
+}  // namespace posefit

@@ -1,0 +1,91 @@
+// Host-compiled window onto csrc/posefit_math.h (the arithmetic the CUDA kernels run per
+// object / per hypothesis), so the CPU test-suite can pin it to the oracle without a GPU.
+// Not part of the product: built on the fly by tests/test_math_host.py with g++.
+#include <cstring>
+#include <vector>
+#include "posefit_math.h"
+
+using namespace posefit;
+
+static void moments_of(const double* src, const double* dst, const int* idx, int n, Moments& m) {
+  std::memset(&m, 0, sizeof(m));
+  for (int k = 0; k < n; ++k) {
+    const int i = idx ? idx[k] : k;
+    const double* x = src + 3 * i;
+    const double* y = dst + 3 * i;
+    m.n += 1.0;
+    for (int a = 0; a < 3; ++a) {
+      m.sx[a] += x[a];
+      m.sy[a] += y[a];
+      m.sxx += x[a] * x[a];
+      for (int b = 0; b < 3; ++b) m.syx[3 * a + b] += y[a] * x[b];
+    }
+  }
+}
+
+static void pack(const Fit& f, double* out) {
+  out[0] = f.s;
+  for (int i = 0; i < 9; ++i) out[1 + i] = f.R[i];
+  for (int i = 0; i < 3; ++i) out[10 + i] = f.t[i];
+  out[13] = f.var;
+  for (int i = 0; i < 6; ++i) out[14 + i] = f.H[i];
+  for (int i = 0; i < 6; ++i) out[20 + i] = f.Linv[i];
+  out[26] = (double)f.status;
+}
+
+extern "C" {
+
+// out[27]: s, R(9), t(3), var, H(6), Linv(6), status
+void pf_check_fit(const double* src, const double* dst, int n, int precise, double* out) {
+  Moments m;
+  moments_of(src, dst, nullptr, n, m);
+  Fit f;
+  if (precise) fit_from_moments<true>(m, f); else fit_from_moments<false>(m, f);
+  pack(f, out);
+}
+
+// residual^2 of every hypothesis (closed form) -- idx[n_hyp][n_samp] into the n points
+void pf_check_hypotheses(const double* src, const double* dst, int n, const int* idx, int n_hyp, int n_samp,
+                         int ref_compat, double* res2) {
+  Moments all;
+  moments_of(src, dst, nullptr, n, all);
+  GlobalStats g;
+  g.n = all.n;
+  for (int a = 0; a < 3; ++a) { g.mux[a] = all.sx[a] / all.n; g.muy[a] = all.sy[a] / all.n; }
+  g.Syy = 0.0;
+  for (int a = 0; a < 9; ++a) g.Syx[a] = 0.0;
+  for (int a = 0; a < 6; ++a) g.Sxx[a] = 0.0;
+  for (int i = 0; i < n; ++i) {
+    double x[3], y[3];
+    for (int a = 0; a < 3; ++a) { x[a] = src[3 * i + a] - g.mux[a]; y[a] = dst[3 * i + a] - g.muy[a]; }
+    g.Syy += y[0] * y[0] + y[1] * y[1] + y[2] * y[2];
+    for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) g.Syx[3 * a + b] += y[a] * x[b];
+    g.Sxx[0] += x[0] * x[0]; g.Sxx[1] += x[0] * x[1]; g.Sxx[2] += x[0] * x[2];
+    g.Sxx[3] += x[1] * x[1]; g.Sxx[4] += x[1] * x[2]; g.Sxx[5] += x[2] * x[2];
+  }
+  for (int h = 0; h < n_hyp; ++h) {
+    Moments m;
+    moments_of(src, dst, idx + (size_t)h * n_samp, n_samp, m);
+    Fit f;
+    fit_from_moments<false>(m, f);
+    double A[9];
+    scoring_transform(f, ref_compat != 0, A);
+    res2[h] = residual_sq(g, A, f.t);
+  }
+}
+
+// adjoint: out[16] = GC(9), gvar, gmux(3), gmuy(3)
+void pf_check_adjoint(const double* src, const double* dst, int n, double gs, const double* gR, const double* gt,
+                      double* out) {
+  Moments m;
+  moments_of(src, dst, nullptr, n, m);
+  Fit f;
+  fit_from_moments<true>(m, f);
+  FitAdjoint a;
+  fit_adjoint(f, gs, gR, gt, a);
+  for (int i = 0; i < 9; ++i) out[i] = a.GC[i];
+  out[9] = a.gvar;
+  for (int i = 0; i < 3; ++i) { out[10 + i] = a.gmux[i]; out[13 + i] = a.gmuy[i]; }
+}
+
+}  // extern "C"
