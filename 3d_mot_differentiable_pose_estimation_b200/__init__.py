@@ -1,1 +1,19 @@
-"""placeholder (filled in below)"""
+"""B200-native per-object 7-DoF pose solver (drop-in for PoseEst/ of
+DomiSchmauser/3D_MOT_Differentiable_Pose_Estimation).
+
+The package name starts with a digit, so import it with
+`importlib.import_module('3d_mot_differentiable_pose_estimation_b200')`.
+
+Layout: `csrc/` holds the sm_100a kernels and the C ABI (include/posefit.h); `function.py` the
+torch.autograd.Function over it; `pose_utils.py` / `pose_estimation.py` mirror the reference's
+own modules (same function names and signatures); `synth.py` makes MOTFront-shaped inputs;
+`shard.py` partitions objects by sequence across GPUs.
+"""
+from . import _lib  # noqa: F401
+from .function import (PoseFit, PoseFitRaw, pose_fit, pose_fit_raw, points_fit_raw,  # noqa: F401
+                       pose_fit_backward_raw, default_kinv,
+                       STATUS_OK, STATUS_EMPTY, STATUS_LOW_INLIER_RATIO, STATUS_NAN)
+from . import synth  # noqa: F401
+
+__all__ = ['PoseFit', 'PoseFitRaw', 'pose_fit', 'pose_fit_raw', 'points_fit_raw', 'pose_fit_backward_raw',
+           'default_kinv', 'synth', 'STATUS_OK', 'STATUS_EMPTY', 'STATUS_LOW_INLIER_RATIO', 'STATUS_NAN']

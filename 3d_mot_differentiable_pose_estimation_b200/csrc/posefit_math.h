@@ -302,8 +302,10 @@ PF_HD void solve_rotation(const double* C, double* R, double* H, double* Linv) {
   for (int i = 0; i < 6; ++i) { H[i] = Hn[i] * m; Linv[i] = Li[i] * inv; }
 }
 
+// ox / oy (optional): origin the sums were shifted by (x - ox, y - oy were accumulated); C and
+// var are shift invariant, the means are restored before t is formed.
 template <bool PRECISE>
-PF_HD void fit_from_moments(const Moments& mo, Fit& f) {
+PF_HD void fit_from_moments(const Moments& mo, Fit& f, const double* ox = nullptr, const double* oy = nullptr) {
   f.n = mo.n;
   f.s = 1.0;
 #pragma unroll
@@ -329,6 +331,10 @@ PF_HD void fit_from_moments(const Moments& mo, Fit& f) {
   if (nan) { f.status = PF_NAN; return; }
   f.var = mo.sxx * rn - (f.mux[0] * f.mux[0] + f.mux[1] * f.mux[1] + f.mux[2] * f.mux[2]);
   solve_rotation<PRECISE>(C, f.R, f.H, f.Linv);
+  if (ox != nullptr) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { f.mux[i] += ox[i]; f.muy[i] += oy[i]; }
+  }
   const double trh = f.H[0] + f.H[3] + f.H[5];           // = sum(D) after the sign fix (:39-42)
   f.s = (f.var * trh != 0.0) ? (1.0 / f.var) * trh : 1.0;   // pose_utils.py:47-50
 #pragma unroll

@@ -1,0 +1,224 @@
+"""Batched pose fit as a torch.autograd.Function over the C-ABI CUDA library.
+
+`PoseFit.apply(noc, depth, mask, bbox_xy0, kinv, sample_idx, ratio_adapt, ref_compat)` is the
+batched operator SURVEY.md section 8b asks for; `pose_fit(...)` is its keyword-friendly face and
+`pose_fit_raw(...)` returns the float64 records exactly as the kernels write them.
+
+What one call replaces in the reference (per object, all of it on the CPU there):
+  run_pose's zero padding + `backproject` + NOC gather (PoseEst/pose_estimation.py:256-290, :323),
+  then `estimateSimilarityUmeyama` (PoseEst/pose_utils.py:16-61) when `sample_idx is None`, or
+  `estimateSimilarityTransform` (pose_utils.py:86-117) with `np.random.randint` (:73) replaced by
+  the host-supplied `sample_idx[b, h, :]`.
+The backward pass has no reference counterpart (the upstream code detaches first,
+Detection/tracker/postprocess.py:151).
+
+PyTorch is plumbing here: it owns device memory and the stream; every computation happens in
+libposefit_b200.so.  Nothing falls back to torch or the CPU: on a non-CUDA tensor the call raises.
+"""
+from __future__ import annotations
+
+from typing import NamedTuple, Optional
+
+import torch
+
+from . import _lib
+
+STATUS_OK, STATUS_EMPTY, STATUS_LOW_INLIER_RATIO, STATUS_NAN = 0, 1, 2, 3
+
+
+class PoseFitRaw(NamedTuple):
+    pose: torch.Tensor          # [B,16] f64: s, R(9, true rotation), t(3), n_fit, ratio, pass_t
+    ctx: torch.Tensor           # [B,32] f64 saved state for backward
+    status: torch.Tensor        # [B] i32
+    n_valid: torch.Tensor       # [B] i32
+    inlier_mask: Optional[torch.Tensor]   # [B,H,W] u8 (RANSAC only)
+    winner: Optional[torch.Tensor]        # [B] i32 (RANSAC only)
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def default_kinv(device=None, height: int = 240, width: int = 320) -> torch.Tensor:
+    """K^-1 of the fixed MOTFront camera run_pose builds (pose_estimation.py:269-288), float64."""
+    from .synth import motfront_intrinsics
+    k = torch.linalg.inv(motfront_intrinsics(height, width))
+    return k.to(device) if device is not None else k
+
+
+def _prep_kinv(kinv, device, n_objects: int):
+    if kinv is None:
+        kinv = default_kinv()
+    kinv = torch.as_tensor(kinv)
+    kinv = kinv.to(device=device, dtype=torch.float64).contiguous()
+    if kinv.shape == (3, 3):
+        return kinv, 0
+    if kinv.shape == (n_objects, 3, 3):
+        return kinv, 1
+    raise ValueError(f'kinv must be [3,3] or [B,3,3], got {tuple(kinv.shape)}')
+
+
+def _check_crops(noc, depth, mask, bbox_xy0):
+    if not noc.is_cuda:
+        raise _lib.PoseFitError('pose_fit needs CUDA tensors: the solver has no CPU path')
+    b, c, h, w = noc.shape
+    if c != 3:
+        raise ValueError('noc must be [B,3,H,W]')
+    if depth.shape != (b, h, w) or mask.shape != (b, h, w) or bbox_xy0.shape != (b, 2):
+        raise ValueError('depth/mask must be [B,H,W] and bbox_xy0 [B,2]')
+    noc = noc.detach().to(torch.float32).contiguous()
+    depth = depth.detach().to(device=noc.device, dtype=torch.float32).contiguous()
+    if mask.dtype == torch.bool:
+        mask = mask.to(torch.uint8)
+    mask = mask.to(device=noc.device, dtype=torch.uint8).contiguous()
+    bbox_xy0 = bbox_xy0.to(device=noc.device, dtype=torch.int32).contiguous()
+    return noc, depth, mask, bbox_xy0, b, h, w
+
+
+def pose_fit_raw(noc, depth, mask, bbox_xy0, kinv=None, sample_idx=None, ratio_adapt: float = 1.0,
+                 ref_compat: bool = True) -> PoseFitRaw:
+    """Forward only, float64 records, no autograd.  Inputs: noc [B,3,H,W] f32 in [0,1],
+    depth [B,H,W] f32, mask [B,H,W] u8/bool, bbox_xy0 [B,2] i32 (x0, y0 of each crop in the frame),
+    kinv [3,3] or [B,3,3] f64 (None = MOTFront camera), sample_idx [B,n_hyp,n_samp] i32 or None."""
+    lib = _lib.lib()
+    noc, depth, mask, bbox_xy0, b, h, w = _check_crops(noc, depth, mask, bbox_xy0)
+    dev = noc.device
+    kinv, per_obj = _prep_kinv(kinv, dev, b)
+    pose = torch.empty(b, _lib.POSE_DOUBLES, dtype=torch.float64, device=dev)
+    ctx = torch.empty(b, _lib.CTX_DOUBLES, dtype=torch.float64, device=dev)
+    status = torch.empty(b, dtype=torch.int32, device=dev)
+    n_valid = torch.empty(b, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        if sample_idx is None:
+            code = lib.posefit_forward(_ptr(noc), _ptr(depth), _ptr(mask), _ptr(bbox_xy0), _ptr(kinv), per_obj,
+                                       b, h, w, _ptr(pose), _ptr(ctx), _ptr(status), _ptr(n_valid), None, 0,
+                                       _stream(dev))
+            _lib.check(code, 'posefit_forward')
+            return PoseFitRaw(pose, ctx, status, n_valid, None, None)
+        sample_idx = sample_idx.to(device=dev, dtype=torch.int32).contiguous()
+        if sample_idx.dim() != 3 or sample_idx.shape[0] != b:
+            raise ValueError('sample_idx must be [B,n_hyp,n_samp]')
+        n_hyp, n_samp = int(sample_idx.shape[1]), int(sample_idx.shape[2])
+        inl = torch.empty(b, h, w, dtype=torch.uint8, device=dev)
+        winner = torch.empty(b, dtype=torch.int32, device=dev)
+        code = lib.posefit_forward_ransac(_ptr(noc), _ptr(depth), _ptr(mask), _ptr(bbox_xy0), _ptr(kinv), per_obj,
+                                          _ptr(sample_idx), b, h, w, n_hyp, n_samp, float(ratio_adapt),
+                                          int(bool(ref_compat)), _ptr(pose), _ptr(ctx), _ptr(status), _ptr(n_valid),
+                                          _ptr(inl), _ptr(winner), None, 0, _stream(dev))
+        _lib.check(code, 'posefit_forward_ransac')
+    return PoseFitRaw(pose, ctx, status, n_valid, inl, winner)
+
+
+def points_fit_raw(src, dst, mask=None, sample_idx=None, ratio_adapt: float = 1.0,
+                   ref_compat: bool = True) -> PoseFitRaw:
+    """Points mode: src/dst [B,3,N] float64 CUDA tensors (rows 0..2 of the reference's [4,N]
+    homogeneous arrays), mask [B,N] u8 (None = all points)."""
+    lib = _lib.lib()
+    if not src.is_cuda:
+        raise _lib.PoseFitError('points_fit needs CUDA tensors: the solver has no CPU path')
+    b, c, n = src.shape
+    if c != 3 or dst.shape != src.shape:
+        raise ValueError('src and dst must both be [B,3,N]')
+    dev = src.device
+    src = src.detach().to(torch.float64).contiguous()
+    dst = dst.detach().to(device=dev, dtype=torch.float64).contiguous()
+    if mask is None:
+        mask = torch.ones(b, n, dtype=torch.uint8, device=dev)
+    mask = mask.to(device=dev, dtype=torch.uint8).contiguous()
+    pose = torch.empty(b, _lib.POSE_DOUBLES, dtype=torch.float64, device=dev)
+    ctx = torch.empty(b, _lib.CTX_DOUBLES, dtype=torch.float64, device=dev)
+    status = torch.empty(b, dtype=torch.int32, device=dev)
+    n_valid = torch.empty(b, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        if sample_idx is None:
+            code = lib.posefit_points_forward(_ptr(src), _ptr(dst), _ptr(mask), b, n, _ptr(pose), _ptr(ctx),
+                                              _ptr(status), _ptr(n_valid), None, 0, _stream(dev))
+            _lib.check(code, 'posefit_points_forward')
+            return PoseFitRaw(pose, ctx, status, n_valid, None, None)
+        sample_idx = sample_idx.to(device=dev, dtype=torch.int32).contiguous()
+        n_hyp, n_samp = int(sample_idx.shape[1]), int(sample_idx.shape[2])
+        inl = torch.empty(b, n, dtype=torch.uint8, device=dev)
+        winner = torch.empty(b, dtype=torch.int32, device=dev)
+        code = lib.posefit_points_forward_ransac(_ptr(src), _ptr(dst), _ptr(mask), _ptr(sample_idx), b, n, n_hyp,
+                                                 n_samp, float(ratio_adapt), int(bool(ref_compat)), _ptr(pose),
+                                                 _ptr(ctx), _ptr(status), _ptr(n_valid), _ptr(inl), _ptr(winner),
+                                                 None, 0, _stream(dev))
+        _lib.check(code, 'posefit_points_forward_ransac')
+    return PoseFitRaw(pose, ctx, status, n_valid, inl, winner)
+
+
+def pose_fit_backward_raw(noc, depth, mask, inlier_mask, bbox_xy0, kinv, ctx, status, grad_scale, grad_R, grad_t,
+                          want_depth_grad: bool = False):
+    """NOC (and optionally depth) gradient from the saved context.  All tensors on one CUDA device."""
+    lib = _lib.lib()
+    noc, depth, mask, bbox_xy0, b, h, w = _check_crops(noc, depth, mask, bbox_xy0)
+    dev = noc.device
+    kinv, per_obj = _prep_kinv(kinv, dev, b)
+
+    def f32(t, shape):
+        if t is None:
+            return None
+        return t.detach().to(device=dev, dtype=torch.float32).reshape(shape).contiguous()
+
+    grad_scale, grad_R, grad_t = f32(grad_scale, (b,)), f32(grad_R, (b, 9)), f32(grad_t, (b, 3))
+    g_noc = torch.empty_like(noc)
+    g_depth = torch.empty_like(depth) if want_depth_grad else None
+    if inlier_mask is not None:
+        inlier_mask = inlier_mask.to(torch.uint8).contiguous()
+    with torch.cuda.device(dev):
+        code = lib.posefit_backward(_ptr(noc), _ptr(depth), _ptr(mask), _ptr(inlier_mask), _ptr(bbox_xy0), _ptr(kinv),
+                                    per_obj, b, h, w, _ptr(ctx), _ptr(status), _ptr(grad_scale), _ptr(grad_R),
+                                    _ptr(grad_t), _ptr(g_noc), _ptr(g_depth), _stream(dev))
+    _lib.check(code, 'posefit_backward')
+    return g_noc, g_depth
+
+
+class PoseFit(torch.autograd.Function):
+    """(scale[B], R[B,3,3], t[B,3], inlier_mask[B,H,W] u8, status[B] i32, n_valid[B] i32) =
+    PoseFit.apply(noc, depth, mask, bbox_xy0, kinv, sample_idx, ratio_adapt, ref_compat).
+
+    R is the true rotation (the reference's `Rotation` is R^T, pose_utils.py:44), so the
+    object-to-camera matrix of run_pose (pose_estimation.py:401-403) is [s*R | t].  Outputs have
+    noc's dtype (float32); `pose_fit_raw` gives the float64 records.  Gradients flow to `noc`
+    and, if it requires grad, to `depth`; the RANSAC selection is a constant."""
+
+    @staticmethod
+    def forward(ctx, noc, depth, mask, bbox_xy0, kinv=None, sample_idx=None, ratio_adapt=1.0, ref_compat=True):
+        raw = pose_fit_raw(noc, depth, mask, bbox_xy0, kinv, sample_idx, ratio_adapt, ref_compat)
+        b, _, h, w = noc.shape
+        inl = raw.inlier_mask
+        ctx.has_inliers = inl is not None
+        ctx.kinv = kinv
+        ctx.depth_grad = bool(depth.requires_grad)
+        ctx.in_dtypes = (noc.dtype, depth.dtype)
+        ctx.save_for_backward(noc, depth, mask, bbox_xy0, raw.ctx, raw.status,
+                              inl if inl is not None else torch.empty(0, device=noc.device))
+        out_dtype = noc.dtype if noc.dtype.is_floating_point else torch.float32
+        scale = raw.pose[:, 0].to(out_dtype)
+        rot = raw.pose[:, 1:10].reshape(b, 3, 3).to(out_dtype)
+        trans = raw.pose[:, 10:13].to(out_dtype)
+        if inl is None:
+            # plain fit: every valid correspondence takes part (mask & depth > 0, pose_estimation.py:23-25)
+            inl = ((mask != 0) & (depth > 0)).to(torch.uint8)
+        ctx.mark_non_differentiable(inl, raw.status, raw.n_valid)
+        return scale, rot, trans, inl, raw.status, raw.n_valid
+
+    @staticmethod
+    def backward(ctx, g_scale, g_rot, g_trans, *_unused):
+        noc, depth, mask, bbox_xy0, saved, status, inl = ctx.saved_tensors
+        g_noc, g_depth = pose_fit_backward_raw(noc, depth, mask, inl if ctx.has_inliers else None, bbox_xy0, ctx.kinv,
+                                               saved, status, g_scale, g_rot, g_trans, ctx.depth_grad)
+        g_noc = g_noc.to(ctx.in_dtypes[0])
+        if g_depth is not None:
+            g_depth = g_depth.to(ctx.in_dtypes[1])
+        return g_noc, g_depth, None, None, None, None, None, None
+
+
+def pose_fit(noc, depth, mask, bbox_xy0, kinv=None, sample_idx=None, ratio_adapt: float = 1.0,
+             ref_compat: bool = True):
+    """Keyword-friendly PoseFit.apply."""
+    return PoseFit.apply(noc, depth, mask, bbox_xy0, kinv, sample_idx, ratio_adapt, ref_compat)

@@ -1,0 +1,411 @@
+#!/usr/bin/env python
+"""bench.py -- object poses/sec (fwd+bwd) of the B200 pose solver, with roofline and CPU baseline.
+
+    python bench.py --gpus N --steps K --warmup W           # our arm (CUDA, through the C ABI)
+    python bench.py --impl reference ...                     # the reference algorithm on host cores
+
+A "step" = one pass of the hot path over this rank's shard of synthetic MOTFront-shaped
+objects: forward (fused mask compaction + back-projection + moments + 3x3 solve) and backward
+(adjoint + NOC-gradient scatter), i.e. BASELINE.json's metric "object poses/sec (fwd+bwd)".
+Workload = the per-GPU shard of BASELINE config 5 at 8 GPUs (625 sequences x 25 frames x 8
+objects = 125,000 objects of 64x64 crops per GPU, sharded by sequence, weak scaling); config 2
+(4096 x 64x64 forward), config 3 (RANSAC, 128 hypotheses) and config 4 (384 x 112x112 fwd+bwd)
+are timed too and reported under "configs".  Inputs are resident in HBM for `value`; `e2e` runs
+the public autograd API from pinned host buffers with the copies inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+PKG = '3d_mot_differentiable_pose_estimation_b200'
+
+SEQ_PER_GPU, FRAMES_PER_SEQ, OBJ_PER_FRAME = 625, 25, 8        # config 5 shard at 8 GPUs
+METRIC = 'object poses/sec (fwd+bwd)'
+UNIT = 'objects/s'
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--objects', type=int, default=SEQ_PER_GPU * FRAMES_PER_SEQ * OBJ_PER_FRAME,
+                    help='objects per GPU per step (default: config-5 shard, 125000)')
+    ap.add_argument('--size', type=int, default=64)
+    ap.add_argument('--e2e-objects', type=int, default=16384)
+    ap.add_argument('--cpu-sample', type=int, default=0, help='objects in the CPU baseline sample (0 = auto)')
+    ap.add_argument('--no-extra', action='store_true', help='skip the config 2/3/4 side measurements')
+    ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU legs (oracle = NumPy restatement of the reference; the reference itself is NumPy)
+# ----------------------------------------------------------------------------------------------
+def _cpu_worker(job):
+    os.environ.setdefault('OMP_NUM_THREADS', '1')
+    import numpy as np
+    import torch
+    torch.set_num_threads(1)
+    from oracle import grad_oracle
+    from oracle import posefit_oracle as po
+    noc, depth, mask, xy0, idx, with_bwd = job
+    t0 = time.perf_counter()
+    n = noc.shape[0]
+    for i in range(n):
+        h, w = depth[i].shape
+        x0, y0 = int(xy0[i, 0]), int(xy0[i, 1])
+        fd = np.zeros((po.FRAME_H, po.FRAME_W), dtype=np.float32)
+        fm = np.zeros((po.FRAME_H, po.FRAME_W), dtype=bool)
+        fd[y0:y0 + h, x0:x0 + w] = depth[i]
+        fm[y0:y0 + h, x0:x0 + w] = mask[i] != 0
+        noc_pts, depth_pts, _ = po.crop_correspondences(np.transpose(noc[i], (1, 2, 0)), fd, fm,
+                                                        (x0, y0, x0 + w, y0 + h))
+        out = po.pose_from_correspondences(noc_pts, depth_pts, None if idx is None else idx[i])
+        if with_bwd and out['status'] == 0:
+            wts = np.zeros(noc_pts.shape[0])
+            wts[out['inlier_idx']] = 1.0
+            grad_oracle.fit_gradients(torch.from_numpy(noc_pts), torch.from_numpy(depth_pts), torch.from_numpy(wts),
+                                      1.0, torch.ones(3, 3, dtype=torch.float64), torch.ones(3, dtype=torch.float64))
+    return n, time.perf_counter() - t0
+
+
+def cpu_objects_per_s(sample, with_bwd=True, ransac=False, procs=None):
+    """Times the oracle over `sample` objects spread over `procs` processes; returns (obj/s, procs)."""
+    import multiprocessing as mp
+    import numpy as np
+    procs = procs or (os.cpu_count() or 1)
+    noc, depth, mask = sample['noc'].numpy(), sample['depth'].numpy(), sample['mask'].numpy()
+    xy0 = sample['bbox_xy0'].numpy()
+    idx = sample['sample_idx'].numpy() if ransac else None
+    n = noc.shape[0]
+    procs = max(1, min(procs, n))
+    cuts = np.linspace(0, n, procs + 1).astype(int)
+    jobs = [(noc[a:b], depth[a:b], mask[a:b], xy0[a:b], None if idx is None else idx[a:b], with_bwd)
+            for a, b in zip(cuts[:-1], cuts[1:]) if b > a]
+    ctx = mp.get_context('spawn')
+    with ctx.Pool(len(jobs)) as pool:
+        pool.map(_cpu_worker, [(noc[:1], depth[:1], mask[:1], xy0[:1], None if idx is None else idx[:1], with_bwd)]
+                 * len(jobs))                                     # import / warm-up
+        t0 = time.perf_counter()
+        pool.map(_cpu_worker, jobs)
+        dt = time.perf_counter() - t0
+    return n / dt, len(jobs)
+
+
+def cpu_baseline(pf, size, n_sample, kind='port'):
+    sample = pf.synth.make_objects(n_sample, size, size, seed=9001)
+    value, cores = cpu_objects_per_s(sample, with_bwd=True)
+    return {'value': value, 'unit': UNIT, 'cores': cores, 'kind': kind,
+            'sample': f'{n_sample} objects of the same {size}x{size} workload, fwd (NumPy restatement of '
+                      f'backproject+Umeyama) + bwd (fp64 torch-autograd restatement), {cores} processes x 1 thread'}
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index=0):
+        self.index, self.samples, self.stop, self.th = index, [], False, None
+
+    def _run(self):
+        while not self.stop:
+            try:
+                out = subprocess.run(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                                      '-i', str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                self.samples.append([x.strip() for x in out.strip().split(',')])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def __enter__(self):
+        self.th = threading.Thread(target=self._run, daemon=True)
+        self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop = True
+        self.th.join(timeout=6)
+
+    def summary(self):
+        import statistics
+        sm = [float(s[0]) for s in self.samples if len(s) >= 6 and s[0].replace('.', '').isdigit()]
+        mx = [float(s[1]) for s in self.samples if len(s) >= 6 and s[1].replace('.', '').isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = sorted({names[j] for s in self.samples if len(s) >= 6 for j in range(4) if s[2 + j] == 'Active'})
+        return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': reasons, 'samples': len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------
+def peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+def time_kernels(fn, steps, warmup, torch):
+    """fn() -> list of (name, start_event, end_event) recorded on the current stream."""
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    acc = {}
+    t_all0 = torch.cuda.Event(enable_timing=True)
+    t_all1 = torch.cuda.Event(enable_timing=True)
+    recs = []
+    t_all0.record()
+    for _ in range(steps):
+        recs.append(fn())
+    t_all1.record()
+    torch.cuda.synchronize()
+    for rec in recs:
+        for name, e0, e1 in rec:
+            acc.setdefault(name, []).append(e0.elapsed_time(e1))
+    return t_all0.elapsed_time(t_all1) / steps, {k: sum(v) / len(v) for k, v in acc.items()}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    pf = importlib.import_module(PKG)
+    lib = pf._lib.lib()
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    hbm_peak, peak_src = peaks()
+    size, n_obj = args.size, args.objects
+    P = size * size
+
+    def ev():
+        return torch.cuda.Event(enable_timing=True)
+
+    # ---- resident shard (sharded by sequence: rank r owns sequences [r*625, (r+1)*625)) ---------
+    d = pf.synth.make_objects(n_obj, size, size, seed=5000 + rank, device=dev)
+    gen = torch.Generator(device=dev).manual_seed(77 + rank)
+    g_s = torch.randn(n_obj, device=dev, generator=gen)
+    g_R = torch.randn(n_obj, 9, device=dev, generator=gen)
+    g_t = torch.randn(n_obj, 3, device=dev, generator=gen)
+    kinv = pf.default_kinv(dev)
+    gathered = torch.empty(world * n_obj, 16, dtype=torch.float64, device=dev) if world > 1 else None
+
+    def step():
+        e0, e1, e2 = ev(), ev(), ev()
+        e0.record()
+        raw = pf.pose_fit_raw(d['noc'], d['depth'], d['mask'], d['bbox_xy0'], kinv)
+        e1.record()
+        pf.pose_fit_backward_raw(d['noc'], d['depth'], d['mask'], None, d['bbox_xy0'], kinv, raw.ctx, raw.status,
+                                 g_s, g_R, g_t)
+        e2.record()
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, raw.pose)      # the one collective: final gather of poses
+        return [('fit_stream_kernel', e0, e1), ('fit_backward_kernel', e1, e2)]
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    launches0 = lib.posefit_launch_count()
+    with ClockSampler(local) as clk:
+        torch.cuda.synchronize()
+        t0, t1 = ev(), ev()
+        t0.record()
+        recs = [step() for _ in range(args.steps)]
+        t1.record()
+        torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    launches = lib.posefit_launch_count() - launches0
+    ms = t0.elapsed_time(t1) / args.steps
+    if world > 1:
+        tms = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms = float(tms)
+    kern = {}
+    for rec in recs:
+        for name, a, b in rec:
+            kern.setdefault(name, []).append(a.elapsed_time(b))
+    kern = {k: sum(v) / len(v) for k, v in kern.items()}
+    value = world * n_obj / (ms * 1e-3)
+
+    # algorithmic bytes per launch: fwd 17 B/px + 64 B pose record (+ 256 B ctx we
+    # actually write is not counted), bwd 29 B/px + 52 B upstream grads + 256 B ctx read
+    bytes_fwd = n_obj * (17 * P + 64)
+    bytes_bwd = n_obj * (29 * P + 52)
+    kernels = {
+        'fit_stream_kernel': {'ms': kern['fit_stream_kernel'], 'algorithmic_bytes': bytes_fwd,
+                              'gbs': bytes_fwd / kern['fit_stream_kernel'] / 1e6},
+        'fit_backward_kernel': {'ms': kern['fit_backward_kernel'], 'algorithmic_bytes': bytes_bwd,
+                                'gbs': bytes_bwd / kern['fit_backward_kernel'] / 1e6},
+    }
+    dom = max(kernels, key=lambda k: kernels[k]['ms'])
+    roofline = {'bound': 'hbm', 'kernel': dom, 'achieved': kernels[dom]['gbs'], 'peak': hbm_peak, 'unit': 'GB/s',
+                'frac': kernels[dom]['gbs'] / hbm_peak, 'traffic': None, 'peak_source': peak_src,
+                'step_achieved': (bytes_fwd + bytes_bwd) / ms / 1e6,
+                'step_frac': (bytes_fwd + bytes_bwd) / ms / 1e6 / hbm_peak, 'kernels': kernels}
+
+    # ---- end to end through the public autograd API from pinned host memory ---------------------
+    ne = min(args.e2e_objects, n_obj)
+    host = {k: d[k][:ne].cpu().pin_memory() for k in ('noc', 'depth', 'mask', 'bbox_xy0')}
+    hg = {'s': g_s[:ne].cpu().pin_memory(), 'R': g_R[:ne].reshape(ne, 3, 3).cpu().pin_memory(),
+          't': g_t[:ne].cpu().pin_memory()}
+    out_host = torch.empty(ne, 13, dtype=torch.float32).pin_memory()
+    h2d = sum(v.numel() * v.element_size() for v in host.values()) + sum(v.numel() * v.element_size() for v in hg.values())
+    d2h = out_host.numel() * 4
+
+    def e2e_step():
+        noc = host['noc'].to(dev, non_blocking=True).requires_grad_(True)
+        depth = host['depth'].to(dev, non_blocking=True)
+        mask = host['mask'].to(dev, non_blocking=True)
+        xy0 = host['bbox_xy0'].to(dev, non_blocking=True)
+        gs, gR, gt = (hg[k].to(dev, non_blocking=True) for k in ('s', 'R', 't'))
+        scale, rot, trans, _, _, _ = pf.pose_fit(noc, depth, mask, xy0, kinv)
+        loss = (scale * gs).sum() + (rot * gR).sum() + (trans * gt).sum()
+        loss.backward()
+        out_host.copy_(torch.cat([scale.detach()[:, None], rot.detach().reshape(ne, 9), trans.detach()], dim=1),
+                       non_blocking=True)
+        return noc.grad
+
+    for _ in range(max(args.warmup, 3)):
+        e2e_step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    k_e2e = max(3, min(args.steps, 10))
+    t0, t1 = ev(), ev()
+    t0.record()
+    for _ in range(k_e2e):
+        e2e_step()
+    t1.record()
+    torch.cuda.synchronize()
+    e2e_ms = t0.elapsed_time(t1) / k_e2e
+    if world > 1:
+        tms = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        e2e_ms = float(tms)
+    e2e = {'value': world * ne / (e2e_ms * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+           'objects_per_step_per_gpu': ne, 'ms_per_step': e2e_ms}
+    del host, hg
+
+    # ---- side measurements: configs 2, 3, 4 (single GPU, rank 0) --------------------------------
+    configs = {}
+    if rank == 0 and not args.no_extra:
+        flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)     # > 126 MB L2
+
+        def timed(fn, reps=10):
+            for _ in range(3):
+                fn()
+            tt = []
+            for _ in range(reps):
+                flush.zero_()
+                a, b = ev(), ev()
+                a.record()
+                fn()
+                b.record()
+                torch.cuda.synchronize()
+                tt.append(a.elapsed_time(b))
+            tt.sort()
+            return tt[len(tt) // 2]
+
+        c2 = pf.synth.make_objects(4096, 64, 64, seed=2000, device=dev, n_hyp=128)
+        ms2 = timed(lambda: pf.pose_fit_raw(c2['noc'], c2['depth'], c2['mask'], c2['bbox_xy0'], kinv))
+        b2 = 4096 * (17 * 4096 + 64)
+        configs['C2 4096x64x64 fwd plain'] = {'ms': ms2, 'objects_per_s': 4096 / ms2 * 1e3, 'gbs': b2 / ms2 / 1e6,
+                                             'frac': b2 / ms2 / 1e6 / hbm_peak}
+        ms3 = timed(lambda: pf.pose_fit_raw(c2['noc'], c2['depth'], c2['mask'], c2['bbox_xy0'], kinv,
+                                            sample_idx=c2['sample_idx']))
+        b3 = 4096 * (17 * 4096 + 64 + 128 * 10 * 4 + 4096)
+        configs['C3 4096x64x64 RANSAC 128 hyp'] = {'ms': ms3, 'objects_per_s': 4096 / ms3 * 1e3, 'gbs': b3 / ms3 / 1e6,
+                                                  'frac': b3 / ms3 / 1e6 / hbm_peak, 'scorer': 'closed-form moments'}
+        c4 = pf.synth.make_objects(384, 112, 112, seed=4000, device=dev)
+        g4 = (torch.randn(384, device=dev), torch.randn(384, 9, device=dev), torch.randn(384, 3, device=dev))
+
+        def c4_step():
+            raw = pf.pose_fit_raw(c4['noc'], c4['depth'], c4['mask'], c4['bbox_xy0'], kinv)
+            pf.pose_fit_backward_raw(c4['noc'], c4['depth'], c4['mask'], None, c4['bbox_xy0'], kinv, raw.ctx,
+                                     raw.status, *g4)
+        ms4 = timed(c4_step)
+        b4 = 384 * (46 * 112 * 112)
+        configs['C4 384x112x112 fwd+bwd'] = {'ms': ms4, 'objects_per_s': 384 / ms4 * 1e3, 'gbs': b4 / ms4 / 1e6,
+                                            'frac': b4 / ms4 / 1e6 / hbm_peak, 'l2_flush_between_iterations': True}
+        del flush, c2, c4
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        n_cpu = args.cpu_sample or 64 * (os.cpu_count() or 1)
+        cpu = cpu_baseline(pf, size, n_cpu)
+
+    if rank == 0:
+        line = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': f'config-5 shard: {n_obj} objects/GPU ({SEQ_PER_GPU} sequences x {FRAMES_PER_SEQ} '
+                                   f'frames x {OBJ_PER_FRAME} objects) x {size}x{size} NOC+depth+mask crops, plain '
+                                   f'Umeyama fit fwd + bwd, sharded by sequence',
+                       'objects_per_gpu': n_obj, 'crop': [size, size],
+                       'l2': 'inputs per step (%.1f GB) exceed the 126 MB L2; no flush needed' % (n_obj * 17 * P / 1e9),
+                       'collective': 'all_gather of 128-B pose records per step' if world > 1 else 'none'},
+            'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': int(launches),
+            'clocks': clk.summary(), 'configs': configs,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', 0))
+    if rank != 0:
+        return
+    pf_synth = importlib.import_module(f'{PKG}.synth')
+    cores = os.cpu_count() or 1
+    n = args.cpu_sample or 32 * cores
+    sample = pf_synth.make_objects(n, args.size, args.size, seed=9001)
+    vals = []
+    for _ in range(max(1, min(args.steps, 3))):
+        v, used = cpu_objects_per_s(sample, with_bwd=True)
+        vals.append(v)
+    value = sorted(vals)[len(vals) // 2]
+    what = (f'{n} objects per step of the same {args.size}x{args.size} workload; oracle port (NumPy restatement of '
+            f'PoseEst backproject + estimateSimilarityUmeyama, fp64) + fp64 autograd backward, {used} processes')
+    line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': n / value * 1e3, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': f'config-5 shard objects, {args.size}x{args.size} crops, plain Umeyama fit fwd + bwd',
+                       'objects_per_step': n},
+            'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': used, 'kind': 'port', 'sample': what},
+            'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}
+    print(json.dumps(line))
+
+
+if __name__ == '__main__':
+    a = parse()
+    if a.impl == 'reference':
+        run_reference(a)
+    else:
+        run_ours(a)

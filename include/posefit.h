@@ -1,0 +1,137 @@
+/* posefit.h -- C ABI of the B200 pose solver (libposefit_b200.so).
+ *
+ * Drop-in boundary for the per-object 7-DoF pose fit of
+ * DomiSchmauser/3D_MOT_Differentiable_Pose_Estimation.  The reference has no FFI for this
+ * path -- it is a set of Python functions called once per detected instance --
+ * so each entry point below cites the reference function(s) whose work it replaces; the
+ * Python side that mirrors the reference's own signatures lives in
+ * 3d_mot_differentiable_pose_estimation_b200/{pose_utils,pose_estimation,function}.py and the
+ * binding a maintainer would add to the reference is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no exceptions.  Every pointer is a DEVICE pointer
+ *     owned by the caller (inputs, outputs and workspace); the library allocates nothing and
+ *     keeps no state except a per-device attribute cache.
+ *   - All calls are asynchronous on `stream` (a cudaStream_t passed as void*), never
+ *     synchronise, never read device data on the host, and are CUDA-graph capturable.
+ *   - Return value: 0 = ok, negative = invalid argument (POSEFIT_E_*), positive = cudaError_t.
+ *   - Layout ("crop layout"): object b owns NOC planes noc[b][3][H][W] (float32, values in
+ *     [0,1]; the reference's HxWx3 patch before its permute, Detection/tracker/postprocess.py:145-147),
+ *     depth[b][H][W] (float32 metres, the bbox window of the frame's depth map,
+ *     PoseEst/pose_estimation.py:260-262), mask[b][H][W] (uint8, the bbox window of the
+ *     instance mask, :290) and bbox_xy0[b] = (x0, y0), the window's top-left pixel in the frame
+ *     (int32), so pixel (i, j) of the crop is frame pixel (u, v) = (x0 + j, y0 + i).
+ *   - kinv: inverse intrinsics, float64 row-major 3x3, either one matrix shared by all objects
+ *     (kinv_per_object = 0) or one per object (= 1)  (np.linalg.inv(intrinsics), pose_estimation.py:22).
+ *   - pose[b][16] (float64): [0] scale s, [1..9] TRUE rotation R row-major (the reference's
+ *     `Rotation` is R^T, PoseEst/pose_utils.py:44), [10..12] translation t, [13] number of
+ *     correspondences in the final fit, [14] inlier ratio as the reference counts it
+ *     (pose_utils.py:10-12, only meaningful for the RANSAC entry), [15] pass threshold PassT.
+ *   - ctx[b][32] (float64): state saved for posefit_backward (R, (tr(H)I-H)^-1, H, s, var, n,
+ *     mu_x, mu_y); opaque to callers.
+ *   - status[b] (int32): 0 ok; 1 no valid correspondence (run_pose returns 6xNone,
+ *     pose_estimation.py:361-362); 2 inlier ratio < 0.1 (4xNone, pose_utils.py:105-107);
+ *     3 NaN covariance (RuntimeError, pose_utils.py:32-36).  For status != 0 the pose is
+ *     (1, I, 0) and all gradients are zero.
+ */
+#ifndef POSEFIT_H_
+#define POSEFIT_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define POSEFIT_ABI_VERSION 1
+#define POSEFIT_POSE_DOUBLES 16
+#define POSEFIT_CTX_DOUBLES 32
+
+#define POSEFIT_E_NULL (-1)       /* a required pointer is NULL */
+#define POSEFIT_E_SHAPE (-2)      /* non-positive or unsupported size */
+#define POSEFIT_E_WORKSPACE (-3)  /* workspace too small */
+#define POSEFIT_E_SMEM (-4)       /* crop does not fit the shared-memory staging of the RANSAC path */
+
+/* ABI version of the loaded library. */
+int posefit_version(void);
+
+/* Human-readable text for a return code of this library (static storage). */
+const char* posefit_error_string(int code);
+
+/* Bytes of device scratch the forward entries need for these sizes (n_hyp = 0 for the
+ * plain fit).  May be 0. */
+size_t posefit_workspace_bytes(int n_objects, int height, int width, int n_hyp, int n_samp);
+
+/* Plain fit on all valid correspondences of every object.
+ * Replaces, per object: the padding + backproject + NOC gather of run_pose
+ * (PoseEst/pose_estimation.py:256-290, :323 and backproject :16-43) followed by
+ * estimateSimilarityUmeyama (PoseEst/pose_utils.py:16-61).  n_valid[b] receives the number of
+ * correspondences (mask != 0 and depth > 0). */
+int posefit_forward(const float* noc, const float* depth, const uint8_t* mask, const int32_t* bbox_xy0,
+                    const double* kinv, int kinv_per_object, int n_objects, int height, int width,
+                    double* pose, double* ctx, int32_t* status, int32_t* n_valid,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* RANSAC fit with host-supplied sample indices.
+ * Replaces, per object: the same front end, then estimateSimilarityTransform
+ * (PoseEst/pose_utils.py:86-117): PassT/StopT heuristics (:91-96), getRANSACInliers (:63-83)
+ * with hypothesis h fitted by estimateSimilarityUmeyama on the n_samp correspondences
+ * sample_idx[b][h][:] (indices into the row-major list of valid pixels, replacing
+ * np.random.randint at :73; values >= n_valid[b] are clamped), scored as evaluateModel does
+ * (:5-14), first-minimum selection with early stop (:76-81), the ratio gate (:105-107) and the
+ * refit on the winner's inliers (:109).
+ * ref_compat != 0 reproduces the reference exactly: hypotheses are scored with the transposed
+ * rotation block the reference builds (:58) and point 0 is never counted as an inlier (:11);
+ * ref_compat == 0 scores with s*R and counts every inlier.
+ * inlier_mask[b][H][W] (uint8) receives the winner's inlier set (all valid pixels when no
+ * hypothesis was accepted); winner[b] (optional, may be NULL) the winning hypothesis or -1. */
+int posefit_forward_ransac(const float* noc, const float* depth, const uint8_t* mask, const int32_t* bbox_xy0,
+                           const double* kinv, int kinv_per_object, const int32_t* sample_idx,
+                           int n_objects, int height, int width, int n_hyp, int n_samp,
+                           double ratio_adapt, int ref_compat,
+                           double* pose, double* ctx, int32_t* status, int32_t* n_valid,
+                           uint8_t* inlier_mask, int32_t* winner,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
+/* Points mode: the same two fits on explicit correspondences, for callers that hold point sets
+ * rather than crops -- the argument form of estimateSimilarityUmeyama / estimateSimilarityTransform
+ * themselves (PoseEst/pose_utils.py:16, :86; run_pose calls them on filtered clouds,
+ * PoseEst/pose_estimation.py:363).  src[b][3][N] is the source cloud (NOC - 0.5), dst[b][3][N]
+ * the target cloud, both float64 planar (rows 0..2 of the reference's homogeneous [4,N] arrays);
+ * mask[b][N] (uint8) selects the points that exist (objects are padded to a common N).
+ * sample_idx indexes the list of selected points.  Outputs as for the crop entries;
+ * inlier_mask is [b][N]. */
+int posefit_points_forward(const double* src, const double* dst, const uint8_t* mask, int n_objects, int n_points,
+                           double* pose, double* ctx, int32_t* status, int32_t* n_valid,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
+int posefit_points_forward_ransac(const double* src, const double* dst, const uint8_t* mask,
+                                  const int32_t* sample_idx, int n_objects, int n_points, int n_hyp, int n_samp,
+                                  double ratio_adapt, int ref_compat,
+                                  double* pose, double* ctx, int32_t* status, int32_t* n_valid,
+                                  uint8_t* inlier_mask, int32_t* winner,
+                                  void* workspace, size_t workspace_bytes, void* stream);
+
+/* Gradient of  sum_b ( grad_scale[b]*s + <grad_R[b], R> + <grad_t[b], t> )  with respect to
+ * the NOC crop (and, when grad_depth != NULL, the depth crop).  No reference function exists:
+ * the upstream code detaches before the fit (Detection/tracker/postprocess.py:151).
+ * inlier_mask may be NULL (plain fit: every valid correspondence has weight 1), otherwise it is
+ * the mask written by posefit_forward_ransac (selection is treated as a constant).
+ * grad_scale [B], grad_R [B][9] (w.r.t. the TRUE rotation), grad_t [B][3] are float32 and may
+ * each be NULL (= zeros).  grad_noc [B][3][H][W] and grad_depth [B][H][W] are fully written. */
+int posefit_backward(const float* noc, const float* depth, const uint8_t* mask, const uint8_t* inlier_mask,
+                     const int32_t* bbox_xy0, const double* kinv, int kinv_per_object,
+                     int n_objects, int height, int width,
+                     const double* ctx, const int32_t* status,
+                     const float* grad_scale, const float* grad_R, const float* grad_t,
+                     float* grad_noc, float* grad_depth, void* stream);
+
+/* Number of kernels this library has launched in the calling process (for bench.py's
+ * gpu_launches claim). */
+unsigned long long posefit_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* POSEFIT_H_ */

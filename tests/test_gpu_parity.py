@@ -1,0 +1,279 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the golden vectors of the real
+reference and against the NumPy oracle on seeded synthetic inputs.
+
+Tolerances (BASELINE.json north_star): inlier masks bit-exact, rotation <= 1e-3 degrees,
+translation and scale <= 1e-5 relative, gradients <= 1e-4 relative (vs the autograd
+restatement -- gradient parity is unpinned, the reference has no backward)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_pkg
+from oracle import grad_oracle
+from oracle import posefit_oracle as po
+
+pytestmark = pytest.mark.gpu
+
+ROT_TOL_DEG = 1e-3
+REL_TOL = 1e-5
+GRAD_TOL = 1e-4
+
+
+@pytest.fixture(scope='module')
+def pf():
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    return load_pkg()
+
+
+def rot_err_deg(ra, rb):
+    return float(np.degrees(np.linalg.norm(ra - rb) / np.sqrt(2)))
+
+
+def _cuda(d, keys=('noc', 'depth', 'mask', 'bbox_xy0', 'sample_idx')):
+    return {k: (torch.from_numpy(np.ascontiguousarray(d[k])).cuda() if isinstance(d[k], np.ndarray) else d[k].cuda())
+            for k in keys if k in d and d[k] is not None}
+
+
+def check_against_oracle(raw, oracle_out, ransac, min_margin=1e-6):
+    pose = raw.pose.cpu().numpy()
+    status = raw.status.cpu().numpy()
+    n_valid = raw.n_valid.cpu().numpy()
+    inl = raw.inlier_mask.cpu().numpy() if raw.inlier_mask is not None else None
+    worst = dict(rot=0.0, t=0.0, s=0.0)
+    n_checked = 0
+    for i, o in enumerate(oracle_out):
+        assert status[i] == o['status'], (i, status[i], o['status'])
+        assert n_valid[i] == o['n_valid'], i
+        if ransac and o['status'] in (0, 2):
+            if o.get('margin', np.inf) < min_margin:
+                continue          # a residual sits on the pass threshold: undecidable in any arithmetic
+            np.testing.assert_array_equal(inl[i], o['inlier_mask'], err_msg=f'object {i}')
+            if o['status'] == 0:
+                assert int(raw.winner[i]) == o['winner'], i
+        if o['status'] != 0:
+            np.testing.assert_array_equal(pose[i, 1:10].reshape(3, 3), np.identity(3))
+            assert pose[i, 0] == 1.0
+            continue
+        n_checked += 1
+        worst['rot'] = max(worst['rot'], rot_err_deg(pose[i, 1:10].reshape(3, 3), o['R']))
+        worst['t'] = max(worst['t'], float(np.linalg.norm(pose[i, 10:13] - o['t']) / np.linalg.norm(o['t'])))
+        worst['s'] = max(worst['s'], abs(pose[i, 0] - o['s']) / abs(o['s']))
+    assert worst['rot'] <= ROT_TOL_DEG, worst
+    assert worst['t'] <= REL_TOL and worst['s'] <= REL_TOL, worst
+    return worst, n_checked
+
+
+@pytest.mark.parametrize('tag,h,w,b', [('c1', 64, 64, 8), ('small', 24, 32, 6), ('odd', 19, 27, 4)])
+def test_golden_frames(pf, golden_dir, tag, h, w, b):
+    """BASELINE config 1 (and two ragged shapes) against outputs of the real reference."""
+    g = np.load(os.path.join(golden_dir, 'frames.npz'))
+    d = {k: g[f'{tag}_{k}'] for k in ('noc', 'depth', 'mask', 'bbox_xy0', 'sample_idx')}
+    t = _cuda(d)
+    plain = pf.pose_fit_raw(t['noc'], t['depth'], t['mask'], t['bbox_xy0'])
+    rans = pf.pose_fit_raw(t['noc'], t['depth'], t['mask'], t['bbox_xy0'], sample_idx=t['sample_idx'])
+    torch.cuda.synchronize()
+    pp, rp = plain.pose.cpu().numpy(), rans.pose.cpu().numpy()
+    for i in range(b):
+        st = int(g[f'{tag}_{i}_status'])
+        assert int(plain.n_valid[i]) == int(g[f'{tag}_{i}_n_valid'])
+        assert int(rans.status[i]) == st
+        if st == 1:
+            assert int(plain.status[i]) == 1
+            continue
+        ref_R = g[f'{tag}_{i}_fit_rotation'].T
+        assert rot_err_deg(pp[i, 1:10].reshape(3, 3), ref_R) <= ROT_TOL_DEG
+        np.testing.assert_allclose(pp[i, 0], g[f'{tag}_{i}_fit_scales'][0], rtol=REL_TOL)
+        np.testing.assert_allclose(pp[i, 10:13], g[f'{tag}_{i}_fit_translation'], rtol=REL_TOL, atol=1e-6)
+        ref_mask = np.unpackbits(g[f'{tag}_{i}_inlier_mask'])[:h * w].reshape(h, w)
+        np.testing.assert_array_equal(rans.inlier_mask[i].cpu().numpy(), ref_mask)
+        np.testing.assert_allclose(rp[i, 15], float(g[f'{tag}_{i}_pass_t']), rtol=1e-6)
+        np.testing.assert_allclose(rp[i, 14], float(g[f'{tag}_{i}_ratio']), rtol=1e-12)
+        if st == 0:
+            ref_R = g[f'{tag}_{i}_ransac_rotation'].T
+            assert rot_err_deg(rp[i, 1:10].reshape(3, 3), ref_R) <= ROT_TOL_DEG
+            np.testing.assert_allclose(rp[i, 0], g[f'{tag}_{i}_ransac_scales'][0], rtol=REL_TOL)
+            np.testing.assert_allclose(rp[i, 10:13], g[f'{tag}_{i}_ransac_translation'], rtol=REL_TOL, atol=1e-6)
+
+
+@pytest.mark.parametrize('h,w,b,seed', [(64, 64, 48, 1), (112, 112, 8, 2), (40, 52, 16, 3), (17, 23, 16, 4)])
+def test_plain_fit_vs_oracle(pf, h, w, b, seed):
+    d = pf.synth.make_objects(b, h, w, seed=seed, align_x0=1 if w % 4 else 4)
+    t = _cuda(d)
+    raw = pf.pose_fit_raw(t['noc'], t['depth'], t['mask'], t['bbox_xy0'])
+    ora = po.batch_pose(d['noc'].numpy(), d['depth'].numpy(), d['mask'].numpy(), d['bbox_xy0'].numpy())
+    worst, n = check_against_oracle(raw, ora, ransac=False)
+    assert n == b
+    print('plain', (h, w), worst)
+
+
+@pytest.mark.parametrize('h,w,b,n_hyp,seed', [(64, 64, 32, 128, 11), (64, 64, 16, 100, 12), (32, 48, 16, 24, 13),
+                                              (21, 30, 8, 17, 14)])
+def test_ransac_fit_vs_oracle(pf, h, w, b, n_hyp, seed):
+    d = pf.synth.make_objects(b, h, w, seed=seed, n_hyp=n_hyp, align_x0=1 if w % 4 else 4)
+    t = _cuda(d)
+    raw = pf.pose_fit_raw(t['noc'], t['depth'], t['mask'], t['bbox_xy0'], sample_idx=t['sample_idx'])
+    ora = po.batch_pose(d['noc'].numpy(), d['depth'].numpy(), d['mask'].numpy(), d['bbox_xy0'].numpy(),
+                        sample_idx=d['sample_idx'].numpy())
+    worst, n = check_against_oracle(raw, ora, ransac=True)
+    assert n >= b - 2
+    margins = [o['margin'] for o in ora if 'margin' in o]
+    print('ransac', (h, w, n_hyp), worst, 'min margin', min(margins))
+
+
+def test_tma_and_fallback_loaders_agree(pf, monkeypatch):
+    d = pf.synth.make_objects(24, 64, 64, seed=21, n_hyp=32)
+    t = _cuda(d)
+    a = pf.pose_fit_raw(t['noc'], t['depth'], t['mask'], t['bbox_xy0'])
+    ar = pf.pose_fit_raw(t['noc'], t['depth'], t['mask'], t['bbox_xy0'], sample_idx=t['sample_idx'])
+    monkeypatch.setenv('POSEFIT_NO_TMA', '1')
+    b_ = pf.pose_fit_raw(t['noc'], t['depth'], t['mask'], t['bbox_xy0'])
+    br = pf.pose_fit_raw(t['noc'], t['depth'], t['mask'], t['bbox_xy0'], sample_idx=t['sample_idx'])
+    torch.cuda.synchronize()
+    assert torch.equal(a.pose, b_.pose) and torch.equal(ar.pose, br.pose)
+    assert torch.equal(ar.inlier_mask, br.inlier_mask)
+
+
+def test_edge_cases(pf):
+    d = pf.synth.make_objects(6, 64, 64, seed=31, n_hyp=16)
+    d['mask'][0] = 0                                  # empty -> status 1 (pose_estimation.py:361-362)
+    d['depth'][1] = 0                                 # no depth -> status 1
+    d['noc'][2, 0, 10, 10] = float('nan')             # NaN -> status 3 (pose_utils.py:32-36)
+    d['mask'][2, 10, 10] = 1
+    d['depth'][2, 10, 10] = 3.0
+    d['mask'][3] = 0
+    d['mask'][3, 20, 20] = 1                          # single correspondence -> scale 1, R = I
+    d['depth'][3, 20, 20] = 3.0
+    t = _cuda(d)
+    raw = pf.pose_fit_raw(t['noc'], t['depth'], t['mask'], t['bbox_xy0'])
+    st = raw.status.cpu().tolist()
+    assert st[:4] == [1, 1, 3, 0] and st[4:] == [0, 0]
+    assert raw.n_valid.cpu().tolist()[:2] == [0, 0] and int(raw.n_valid[3]) == 1
+    p3 = raw.pose[3].cpu().numpy()
+    assert p3[0] == 1.0 and np.array_equal(p3[1:10].reshape(3, 3), np.identity(3))
+    rr = pf.pose_fit_raw(t['noc'], t['depth'], t['mask'], t['bbox_xy0'], sample_idx=t['sample_idx'])
+    assert rr.status.cpu().tolist()[:2] == [1, 1]
+    # zero hypotheses: nothing accepted, BestInlierRatio stays 0 -> 4xNone (pose_utils.py:68-70,105)
+    z = pf.pose_fit_raw(t['noc'][4:], t['depth'][4:], t['mask'][4:], t['bbox_xy0'][4:],
+                        sample_idx=torch.zeros(2, 0, 10, dtype=torch.int32, device='cuda'))
+    assert z.status.cpu().tolist() == [2, 2] and z.winner.cpu().tolist() == [-1, -1]
+
+
+def test_ref_compat_switch(pf):
+    d = pf.synth.make_objects(8, 64, 64, seed=41, n_hyp=64)
+    t = _cuda(d)
+    a = pf.pose_fit_raw(t['noc'], t['depth'], t['mask'], t['bbox_xy0'], sample_idx=t['sample_idx'], ref_compat=True)
+    b = pf.pose_fit_raw(t['noc'], t['depth'], t['mask'], t['bbox_xy0'], sample_idx=t['sample_idx'], ref_compat=False)
+    # with the geometrically correct scoring the winner fits the clean data: inliers = non-outliers,
+    # and the recovered pose is close to the generating one
+    for i in range(8):
+        assert int(b.status[i]) == 0
+        R = b.pose[i, 1:10].reshape(3, 3).cpu().numpy()
+        assert rot_err_deg(R, d['gt_R'][i].numpy()) < 2.0
+    assert not torch.equal(a.winner, b.winner)
+
+
+def test_points_mode_vs_oracle(pf):
+    rng = np.random.default_rng(5)
+    b, n, n_hyp = 12, 704, 40
+    src = rng.uniform(-0.5, 0.5, size=(b, n, 3))
+    dst = np.empty_like(src)
+    mask = np.ones((b, n), dtype=np.uint8)
+    idx = np.zeros((b, n_hyp, 10), dtype=np.int32)
+    for i in range(b):
+        rot = np.linalg.qr(rng.normal(size=(3, 3)))[0]
+        dst[i] = rng.uniform(0.6, 2.2) * src[i] @ rot.T + np.array([0.3, -0.2, -3.5]) + rng.normal(scale=0.01, size=(n, 3))
+        bad = rng.uniform(size=n) < 0.1
+        dst[i, bad, 2] -= rng.uniform(25, 40, size=bad.sum())
+        nv = n - 16 * i
+        mask[i, nv:] = 0
+        idx[i] = rng.integers(0, nv, size=(n_hyp, 10))
+    s_t = torch.from_numpy(np.ascontiguousarray(src.transpose(0, 2, 1))).cuda()
+    d_t = torch.from_numpy(np.ascontiguousarray(dst.transpose(0, 2, 1))).cuda()
+    m_t = torch.from_numpy(mask).cuda()
+    plain = pf.points_fit_raw(s_t, d_t, m_t)
+    rans = pf.points_fit_raw(s_t, d_t, m_t, sample_idx=torch.from_numpy(idx).cuda())
+    pp, rp = plain.pose.cpu().numpy(), rans.pose.cpu().numpy()
+    for i in range(b):
+        nv = n - 16 * i
+        scales, rot_t, trans, _ = po.umeyama_fit(src[i, :nv], dst[i, :nv])
+        assert rot_err_deg(pp[i, 1:10].reshape(3, 3), rot_t.T) < 1e-7
+        np.testing.assert_allclose(pp[i, 0], scales[0], rtol=1e-9)
+        np.testing.assert_allclose(pp[i, 10:13], trans, rtol=1e-9)
+        o = po.similarity_transform(src[i, :nv], dst[i, :nv], idx[i])
+        assert o['ok'] and int(rans.status[i]) == 0
+        want = np.zeros(n, dtype=np.uint8)
+        want[o['inlier_idx']] = 1
+        np.testing.assert_array_equal(rans.inlier_mask[i].cpu().numpy(), want)
+        assert rot_err_deg(rp[i, 1:10].reshape(3, 3), o['rot_t'].T) < 1e-7
+        np.testing.assert_allclose(rp[i, 0], o['scales'][0], rtol=1e-9)
+
+
+@pytest.mark.parametrize('h,w,with_ransac', [(64, 64, False), (64, 64, True), (112, 112, False), (18, 22, False)])
+def test_backward_vs_autograd_oracle(pf, h, w, with_ransac):
+    b = 6
+    d = pf.synth.make_objects(b, h, w, seed=51, n_hyp=48 if with_ransac else 0, align_x0=1 if w % 4 else 4)
+    t = _cuda(d)
+    noc = t['noc'].clone().requires_grad_(True)
+    depth = t['depth'].clone().requires_grad_(True)
+    out = pf.pose_fit(noc, depth, t['mask'], t['bbox_xy0'], sample_idx=t.get('sample_idx'))
+    scale, rot, trans, inl, status, n_valid = out
+    gen = torch.Generator().manual_seed(7)
+    g_s = torch.randn(b, generator=gen)
+    g_R = torch.randn(b, 3, 3, generator=gen)
+    g_t = torch.randn(b, 3, generator=gen)
+    loss = (scale * g_s.cuda()).sum() + (rot * g_R.cuda()).sum() + (trans * g_t.cuda()).sum()
+    loss.backward()
+    g_noc = noc.grad.cpu().numpy()
+    g_depth = depth.grad.cpu().numpy()
+    inl = inl.cpu().numpy()
+    k_mat = po.motfront_intrinsics()
+    for i in range(b):
+        assert int(status[i]) == 0
+        x0, y0 = (int(v) for v in d['bbox_xy0'][i])
+        frame_d = np.zeros((240, 320), dtype=np.float32)
+        frame_m = np.zeros((240, 320), dtype=bool)
+        frame_d[y0:y0 + h, x0:x0 + w] = d['depth'][i].numpy()
+        frame_m[y0:y0 + h, x0:x0 + w] = d['mask'][i].numpy() != 0
+        noc_pts, depth_pts, (rows, cols) = po.crop_correspondences(
+            np.transpose(d['noc'][i].numpy(), (1, 2, 0)), frame_d, frame_m, (x0, y0, x0 + w, y0 + h), k_mat)
+        wts = inl[i][rows - y0, cols - x0].astype(np.float64)
+        gx, gy, _ = grad_oracle.fit_gradients(torch.from_numpy(noc_pts), torch.from_numpy(depth_pts),
+                                              torch.from_numpy(wts), g_s[i].double(), g_R[i].double(), g_t[i].double())
+        want = np.zeros((3, h, w))
+        want[:, rows - y0, cols - x0] = gx.numpy().T
+        scale_ref = np.abs(want).max()
+        err = np.abs(g_noc[i] - want).max() / scale_ref
+        assert err <= GRAD_TOL, (i, err)
+        # depth gradient: y = (rx z, -ry z, -z)
+        rx = (cols - k_mat[0, 2]) / k_mat[0, 0]
+        ry = (rows - k_mat[1, 2]) / k_mat[1, 1]
+        gz = gy.numpy()[:, 0] * rx - gy.numpy()[:, 1] * ry - gy.numpy()[:, 2]
+        want_z = np.zeros((h, w))
+        want_z[rows - y0, cols - x0] = gz
+        errz = np.abs(g_depth[i] - want_z).max() / max(np.abs(want_z).max(), 1e-30)
+        assert errz <= GRAD_TOL, (i, errz)
+
+
+def test_full_size_properties(pf):
+    """BASELINE config 2 size (4096 x 64x64): properties that need no oracle -- orthonormal R,
+    det +1, scale/translation equivariance of the fit under a rigid change of the NOC frame."""
+    b = 4096
+    d = pf.synth.make_objects(b, 64, 64, seed=61, device='cuda')
+    raw = pf.pose_fit_raw(d['noc'], d['depth'], d['mask'], d['bbox_xy0'])
+    assert int((raw.status != 0).sum()) == 0
+    R = raw.pose[:, 1:10].reshape(b, 3, 3)
+    eye = torch.eye(3, dtype=torch.float64, device='cuda')
+    assert float((R @ R.transpose(1, 2) - eye).abs().max()) < 1e-12
+    assert float((torch.linalg.det(R) - 1).abs().max()) < 1e-12
+    assert torch.equal(raw.n_valid, d['n_valid'])
+    # recovered pose close to the generating one on the clean 90% (outliers bias it, so loose bounds)
+    # permuting NOC channels permutes the columns of R: fit(noc[:, perm]) == fit(noc) with R[:, perm]
+    perm = [2, 0, 1]
+    raw2 = pf.pose_fit_raw(d['noc'][:, perm].contiguous(), d['depth'], d['mask'], d['bbox_xy0'])
+    R2 = raw2.pose[:, 1:10].reshape(b, 3, 3)
+    assert float((R2 - R[:, :, perm]).abs().max()) < 1e-9
+    assert float((raw2.pose[:, 0] - raw.pose[:, 0]).abs().max() / raw.pose[:, 0].abs().max()) < 1e-12
+    assert float((raw2.pose[:, 10:13] - raw.pose[:, 10:13]).abs().max()) < 1e-9
