@@ -43,6 +43,12 @@ def _stream(device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
 
+def _workspace(lib, dev, b: int, h: int, w: int) -> torch.Tensor:
+    """Caller-owned scratch for the plain fit (partial moments), sized by the library."""
+    nbytes = int(lib.posefit_workspace_bytes(b, h, w, 0, 0))
+    return torch.empty(max(nbytes, 8), dtype=torch.uint8, device=dev)
+
+
 def default_kinv(device=None, height: int = 240, width: int = 320) -> torch.Tensor:
     """K^-1 of the fixed MOTFront camera run_pose builds (pose_estimation.py:269-288), float64."""
     from .synth import motfront_intrinsics
@@ -94,9 +100,10 @@ def pose_fit_raw(noc, depth, mask, bbox_xy0, kinv=None, sample_idx=None, ratio_a
     n_valid = torch.empty(b, dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
         if sample_idx is None:
+            ws = _workspace(lib, dev, b, h, w)
             code = lib.posefit_forward(_ptr(noc), _ptr(depth), _ptr(mask), _ptr(bbox_xy0), _ptr(kinv), per_obj,
-                                       b, h, w, _ptr(pose), _ptr(ctx), _ptr(status), _ptr(n_valid), None, 0,
-                                       _stream(dev))
+                                       b, h, w, _ptr(pose), _ptr(ctx), _ptr(status), _ptr(n_valid), _ptr(ws),
+                                       ws.numel(), _stream(dev))
             _lib.check(code, 'posefit_forward')
             return PoseFitRaw(pose, ctx, status, n_valid, None, None)
         sample_idx = sample_idx.to(device=dev, dtype=torch.int32).contiguous()
@@ -135,8 +142,9 @@ def points_fit_raw(src, dst, mask=None, sample_idx=None, ratio_adapt: float = 1.
     n_valid = torch.empty(b, dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
         if sample_idx is None:
+            ws = _workspace(lib, dev, b, 1, n)
             code = lib.posefit_points_forward(_ptr(src), _ptr(dst), _ptr(mask), b, n, _ptr(pose), _ptr(ctx),
-                                              _ptr(status), _ptr(n_valid), None, 0, _stream(dev))
+                                              _ptr(status), _ptr(n_valid), _ptr(ws), ws.numel(), _stream(dev))
             _lib.check(code, 'posefit_points_forward')
             return PoseFitRaw(pose, ctx, status, n_valid, None, None)
         sample_idx = sample_idx.to(device=dev, dtype=torch.int32).contiguous()

@@ -161,18 +161,44 @@ def test_edge_cases(pf):
     assert z.status.cpu().tolist() == [2, 2] and z.winner.cpu().tolist() == [-1, -1]
 
 
+def _noncompat_reference(src, dst, idx):
+    """ref_compat=False (our extension, not a reference mode): score every hypothesis with the
+    geometrically correct [s*R | t] and count every inlier; otherwise pose_utils.py:63-117."""
+    pass_t, stop_t = po.pass_thresholds(src, dst)
+    best, best_inl = 1e10, np.arange(src.shape[0])
+    win = -1
+    for h in range(idx.shape[0]):
+        scales, rot_t, trans, _ = po.umeyama_fit(src[idx[h]], dst[idx[h]])
+        r = np.linalg.norm(dst.T - (scales[0] * rot_t.T @ src.T + trans[:, None]), axis=0)
+        res = np.linalg.norm(r)
+        if res < best:
+            best, best_inl, win = res, np.where(r < pass_t)[0], h
+        if best < stop_t:
+            break
+    return win, best_inl
+
+
 def test_ref_compat_switch(pf):
-    d = pf.synth.make_objects(8, 64, 64, seed=41, n_hyp=64)
+    b, h, w = 8, 64, 64
+    d = pf.synth.make_objects(b, h, w, seed=41, n_hyp=64, outlier_range=(80.0, 120.0))
     t = _cuda(d)
     a = pf.pose_fit_raw(t['noc'], t['depth'], t['mask'], t['bbox_xy0'], sample_idx=t['sample_idx'], ref_compat=True)
-    b = pf.pose_fit_raw(t['noc'], t['depth'], t['mask'], t['bbox_xy0'], sample_idx=t['sample_idx'], ref_compat=False)
-    # with the geometrically correct scoring the winner fits the clean data: inliers = non-outliers,
-    # and the recovered pose is close to the generating one
-    for i in range(8):
-        assert int(b.status[i]) == 0
-        R = b.pose[i, 1:10].reshape(3, 3).cpu().numpy()
-        assert rot_err_deg(R, d['gt_R'][i].numpy()) < 2.0
-    assert not torch.equal(a.winner, b.winner)
+    c = pf.pose_fit_raw(t['noc'], t['depth'], t['mask'], t['bbox_xy0'], sample_idx=t['sample_idx'], ref_compat=False)
+    assert not torch.equal(a.winner, c.winner)
+    for i in range(b):
+        x0, y0 = (int(v) for v in d['bbox_xy0'][i])
+        fd = np.zeros((240, 320), dtype=np.float32)
+        fm = np.zeros((240, 320), dtype=bool)
+        fd[y0:y0 + h, x0:x0 + w] = d['depth'][i].numpy()
+        fm[y0:y0 + h, x0:x0 + w] = d['mask'][i].numpy() != 0
+        src, dst, (rows, cols) = po.crop_correspondences(np.transpose(d['noc'][i].numpy(), (1, 2, 0)), fd, fm,
+                                                         (x0, y0, x0 + w, y0 + h))
+        win, inl = _noncompat_reference(src, dst, d['sample_idx'][i].numpy())
+        assert int(c.winner[i]) == win
+        want = np.zeros((h, w), dtype=np.uint8)
+        want[rows[inl] - y0, cols[inl] - x0] = 1
+        np.testing.assert_array_equal(c.inlier_mask[i].cpu().numpy(), want)
+        assert abs(float(c.pose[i, 14]) - len(inl) / src.shape[0]) < 1e-15      # every inlier is counted
 
 
 def test_points_mode_vs_oracle(pf):
