@@ -13,7 +13,8 @@ from . import _lib  # noqa: F401
 from .function import (PoseFit, PoseFitRaw, pose_fit, pose_fit_raw, points_fit_raw,  # noqa: F401
                        pose_fit_backward_raw, default_kinv,
                        STATUS_OK, STATUS_EMPTY, STATUS_LOW_INLIER_RATIO, STATUS_NAN)
-from . import synth  # noqa: F401
+from . import synth, shard  # noqa: F401
+from . import pose_utils, pose_estimation  # noqa: F401  (drop-ins for PoseEst/pose_utils.py, pose_estimation.py)
 
 __all__ = ['PoseFit', 'PoseFitRaw', 'pose_fit', 'pose_fit_raw', 'points_fit_raw', 'pose_fit_backward_raw',
            'default_kinv', 'synth', 'STATUS_OK', 'STATUS_EMPTY', 'STATUS_LOW_INLIER_RATIO', 'STATUS_NAN']

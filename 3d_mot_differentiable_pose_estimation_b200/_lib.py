@@ -22,7 +22,8 @@ ABI_VERSION = 1
 # every symbol include/posefit.h declares
 SYMBOLS = ('posefit_version', 'posefit_error_string', 'posefit_workspace_bytes', 'posefit_forward',
            'posefit_forward_ransac', 'posefit_backward', 'posefit_launch_count',
-           'posefit_points_forward', 'posefit_points_forward_ransac')
+           'posefit_points_forward', 'posefit_points_forward_ransac', 'posefit_compact',
+           'posefit_points_evaluate', 'posefit_transform_points')
 
 _lock = threading.Lock()
 _lib = None
@@ -70,8 +71,14 @@ def _declare(lib):
     lib.posefit_points_forward.restype = i32
     lib.posefit_points_forward.argtypes = [vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, sz, vp]
     lib.posefit_points_forward_ransac.restype = i32
-    lib.posefit_points_forward_ransac.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, f64, i32,
+    lib.posefit_points_forward_ransac.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, f64, f64, f64, i32,
                                                   vp, vp, vp, vp, vp, vp, vp, sz, vp]
+    lib.posefit_compact.restype = i32
+    lib.posefit_compact.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp]
+    lib.posefit_points_evaluate.restype = i32
+    lib.posefit_points_evaluate.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp]
+    lib.posefit_transform_points.restype = i32
+    lib.posefit_transform_points.argtypes = [vp, i32, vp, vp, i32, i32, vp]
 
 
 def lib():

@@ -52,7 +52,7 @@ def _workspace(lib, dev, b: int, h: int, w: int) -> torch.Tensor:
 def default_kinv(device=None, height: int = 240, width: int = 320) -> torch.Tensor:
     """K^-1 of the fixed MOTFront camera run_pose builds (pose_estimation.py:269-288), float64."""
     from .synth import motfront_intrinsics
-    k = torch.linalg.inv(motfront_intrinsics(height, width))
+    k = torch.linalg.inv(motfront_intrinsics(height, width)).contiguous()   # inv may return column-major strides
     return k.to(device) if device is not None else k
 
 
@@ -121,7 +121,7 @@ def pose_fit_raw(noc, depth, mask, bbox_xy0, kinv=None, sample_idx=None, ratio_a
 
 
 def points_fit_raw(src, dst, mask=None, sample_idx=None, ratio_adapt: float = 1.0,
-                   ref_compat: bool = True) -> PoseFitRaw:
+                   ref_compat: bool = True, pass_threshold: float = 0.0, stop_threshold: float = 0.0) -> PoseFitRaw:
     """Points mode: src/dst [B,3,N] float64 CUDA tensors (rows 0..2 of the reference's [4,N]
     homogeneous arrays), mask [B,N] u8 (None = all points)."""
     lib = _lib.lib()
@@ -152,7 +152,8 @@ def points_fit_raw(src, dst, mask=None, sample_idx=None, ratio_adapt: float = 1.
         inl = torch.empty(b, n, dtype=torch.uint8, device=dev)
         winner = torch.empty(b, dtype=torch.int32, device=dev)
         code = lib.posefit_points_forward_ransac(_ptr(src), _ptr(dst), _ptr(mask), _ptr(sample_idx), b, n, n_hyp,
-                                                 n_samp, float(ratio_adapt), int(bool(ref_compat)), _ptr(pose),
+                                                 n_samp, float(ratio_adapt), float(pass_threshold),
+                                                 float(stop_threshold), int(bool(ref_compat)), _ptr(pose),
                                                  _ptr(ctx), _ptr(status), _ptr(n_valid), _ptr(inl), _ptr(winner),
                                                  None, 0, _stream(dev))
         _lib.check(code, 'posefit_points_forward_ransac')

@@ -1,0 +1,50 @@
+"""Multi-GPU partitioning of the pose path.
+
+Objects are independent, so the path shards with no data-path collective: sequences (25 frames,
+Detection/train_combined.py:128-129, :237-246) are dealt out in contiguous blocks, every rank fits
+the objects of its own sequences on its own GPU, and ONE all-gather of the 128-byte pose records
+makes the result visible everywhere (the reference only ever gathers python prediction lists,
+Detection/evaluator/FrontEvaluator.py:143).  Gradients stay with the rank that owns the NOC crop.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def sequence_shard(n_sequences: int, rank: int, world_size: int) -> Tuple[int, int]:
+    """[start, end) of the whole sequences owned by `rank`; sizes differ by at most one."""
+    if not (0 <= rank < world_size):
+        raise ValueError('rank out of range')
+    base, rem = divmod(n_sequences, world_size)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+def object_range(seq_offsets: torch.Tensor, rank: int, world_size: int) -> Tuple[int, int]:
+    """seq_offsets: [n_sequences + 1] prefix of objects per sequence (objects are stored sequence
+    by sequence).  Returns the contiguous object range of this rank's sequences."""
+    s0, s1 = sequence_shard(int(seq_offsets.numel()) - 1, rank, world_size)
+    return int(seq_offsets[s0]), int(seq_offsets[s1])
+
+
+def gather_poses(local: torch.Tensor, counts: Optional[list] = None, group=None) -> torch.Tensor:
+    """All-gather per-rank pose records [n_r, 16] into [sum n_r, 16] in rank order.
+    counts: objects per rank when shards are ragged (None = equal shards)."""
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return local
+    world = dist.get_world_size(group)
+    if counts is None:
+        out = torch.empty((world * local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(out, local.contiguous(), group=group)
+        return out
+    if len(counts) != world or counts[dist.get_rank(group)] != local.shape[0]:
+        raise ValueError('counts must list the shard size of every rank')
+    width = max(counts)
+    padded = torch.zeros((width,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    padded[:local.shape[0]] = local
+    out = torch.empty((world * width,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, padded, group=group)
+    return torch.cat([out[r * width:r * width + counts[r]] for r in range(world)], dim=0)

@@ -126,11 +126,3 @@ def make_objects(n_objects: int, height: int = 64, width: int = 64, *, seed: int
             out['sample_idx'][sl] = idx.to(torch.int32)
         del is_out, push, z, m
     return out
-
-
-def sequence_shard(n_sequences: int, rank: int, world_size: int):
-    """Contiguous range of whole sequences owned by `rank` (shard by
-    sequence, 25 frames each -- train_combined.py:128-129)."""
-    base, rem = divmod(n_sequences, world_size)
-    start = rank * base + min(rank, rem)
-    return start, start + base + (1 if rank < rem else 0)

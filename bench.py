@@ -208,7 +208,6 @@ def run_ours(args):
     g_R = torch.randn(n_obj, 9, device=dev, generator=gen)
     g_t = torch.randn(n_obj, 3, device=dev, generator=gen)
     kinv = pf.default_kinv(dev)
-    gathered = torch.empty(world * n_obj, 16, dtype=torch.float64, device=dev) if world > 1 else None
 
     def step():
         e0, e1, e2 = ev(), ev(), ev()
@@ -219,7 +218,7 @@ def run_ours(args):
                                  g_s, g_R, g_t)
         e2.record()
         if world > 1:
-            dist.all_gather_into_tensor(gathered, raw.pose)      # the one collective: final gather of poses
+            pf.shard.gather_poses(raw.pose)                      # the one collective: final gather of poses
         return [('fit_stream_kernel', e0, e1), ('fit_backward_kernel', e1, e2)]
 
     for _ in range(args.warmup):

@@ -101,14 +101,16 @@ int posefit_forward_ransac(const float* noc, const float* depth, const uint8_t* 
  * the target cloud, both float64 planar (rows 0..2 of the reference's homogeneous [4,N] arrays);
  * mask[b][N] (uint8) selects the points that exist (objects are padded to a common N).
  * sample_idx indexes the list of selected points.  Outputs as for the crop entries;
- * inlier_mask is [b][N]. */
+ * inlier_mask is [b][N].  pass_threshold / stop_threshold > 0 replace the data-derived PassT /
+ * StopT (the explicit arguments of getRANSACInliers, pose_utils.py:63); pass <= 0 to derive them. */
 int posefit_points_forward(const double* src, const double* dst, const uint8_t* mask, int n_objects, int n_points,
                            double* pose, double* ctx, int32_t* status, int32_t* n_valid,
                            void* workspace, size_t workspace_bytes, void* stream);
 
 int posefit_points_forward_ransac(const double* src, const double* dst, const uint8_t* mask,
                                   const int32_t* sample_idx, int n_objects, int n_points, int n_hyp, int n_samp,
-                                  double ratio_adapt, int ref_compat,
+                                  double ratio_adapt, double pass_threshold, double stop_threshold,
+                                  int ref_compat,
                                   double* pose, double* ctx, int32_t* status, int32_t* n_valid,
                                   uint8_t* inlier_mask, int32_t* winner,
                                   void* workspace, size_t workspace_bytes, void* stream);
@@ -126,6 +128,29 @@ int posefit_backward(const float* noc, const float* depth, const uint8_t* mask, 
                      const double* ctx, const int32_t* status,
                      const float* grad_scale, const float* grad_R, const float* grad_t,
                      float* grad_noc, float* grad_depth, void* stream);
+
+/* Stable row-major compaction of every crop: the correspondences exactly as the reference builds
+ * them before the fit -- `backproject` (PoseEst/pose_estimation.py:16-43: points and the np.where
+ * index arrays) and the NOC gather of run_pose (:323).  Frame-level use: one "crop" = the whole
+ * frame, bbox (0,0).  dst[b][P][3] / src[b][P][3] (float64, interleaved like the reference's [N,3]
+ * arrays; src and noc may be NULL), rows/cols[b][P] frame coordinates (int32), count[b].  Only the
+ * first count[b] entries of each object are written. */
+int posefit_compact(const float* noc, const float* depth, const uint8_t* mask, const int32_t* bbox_xy0,
+                    const double* kinv, int kinv_per_object, int n_objects, int height, int width,
+                    double* src, double* dst, int32_t* rows, int32_t* cols, int32_t* count, void* stream);
+
+/* evaluateModel (PoseEst/pose_utils.py:5-14) for one explicit 4x4 row-major transform per object on
+ * points-mode inputs.  stats[b][4] = { Residual, number of inliers, 1 if the first selected point is
+ * an inlier (the reference's count_nonzero skips it, :11), number of selected points };
+ * inlier_mask[b][N].  pass_threshold: one value (pass_per_object = 0) or one per object. */
+int posefit_points_evaluate(const double* transform, const double* src, const double* dst, const uint8_t* mask,
+                            const double* pass_threshold, int pass_per_object, int n_objects, int n_points,
+                            double* stats, uint8_t* inlier_mask, void* stream);
+
+/* out = A p + t on interleaved float64 [N][3] points, matrix = [A | t] row-major 3x4 (one, or one
+ * per object): transform_pc (PoseEst/pose_estimation.py:45-57) and cam2world (:59-70). */
+int posefit_transform_points(const double* matrix, int matrix_per_object, const double* points, double* out,
+                             int n_objects, int n_points, void* stream);
 
 /* Number of kernels this library has launched in the calling process (for bench.py's
  * gpu_launches claim). */

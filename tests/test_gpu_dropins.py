@@ -1,0 +1,170 @@
+"""The same-named drop-ins (pose_utils.py / pose_estimation.py of the package) against the golden
+vectors written from the REAL reference functions of the same name."""
+import contextlib
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_pkg
+from oracle import posefit_oracle as po
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def pf():
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    return load_pkg()
+
+
+def _hom(p):
+    return np.transpose(np.hstack([p, np.ones([p.shape[0], 1])]))
+
+
+def rot_err_deg(ra, rb):
+    return float(np.degrees(np.linalg.norm(ra - rb) / np.sqrt(2)))
+
+
+@contextlib.contextmanager
+def replay(idx):
+    """np.random.randint(n, size=(n_iter, 10)) -> the stored indices (what the reference drew)."""
+    real = np.random.randint
+
+    def fake(high, size=None, **kw):
+        assert tuple(size) == idx.shape and idx.max() < high
+        return idx.copy()
+
+    np.random.randint = fake
+    try:
+        yield
+    finally:
+        np.random.randint = real
+
+
+def test_estimateSimilarityUmeyama(pf, golden_dir):
+    g = np.load(os.path.join(golden_dir, 'umeyama.npz'))
+    for k, name in enumerate(str(n) for n in g['names']):
+        if name in ('roundoff_variance', 'single_point'):
+            continue
+        scales, rot, trans, tf = pf.pose_utils.estimateSimilarityUmeyama(_hom(g[f'src_{k}']), _hom(g[f'dst_{k}']))
+        assert rot_err_deg(rot, g[f'rotation_{k}']) < 1e-6, name
+        np.testing.assert_allclose(scales, g[f'scales_{k}'], rtol=1e-9, err_msg=name)
+        np.testing.assert_allclose(trans, g[f'translation_{k}'], rtol=1e-9, atol=1e-9, err_msg=name)
+        np.testing.assert_allclose(tf, g[f'transform_{k}'], rtol=1e-8, atol=1e-8, err_msg=name)
+    bad = np.ones((4, 6))
+    bad[1, 2] = np.nan
+    with pytest.raises(RuntimeError, match='NANs'):
+        pf.pose_utils.estimateSimilarityUmeyama(bad, np.ones((4, 6)))
+
+
+def test_evaluateModel(pf, golden_dir):
+    g = np.load(os.path.join(golden_dir, 'evaluate.npz'))
+    for k in range(int(g['count'])):
+        res, ratio, idx = pf.pose_utils.evaluateModel(g[f'transform_{k}'], _hom(g[f'src_{k}']), _hom(g[f'dst_{k}']),
+                                                      float(g[f'pass_{k}']))
+        np.testing.assert_allclose(res, g[f'residual_{k}'], rtol=1e-12)
+        assert ratio == float(g[f'ratio_{k}'])
+        np.testing.assert_array_equal(idx, g[f'idx_{k}'])
+
+
+def test_getRANSACInliers(pf, golden_dir):
+    g = np.load(os.path.join(golden_dir, 'ransac_inliers.npz'))
+    for k in range(int(g['count'])):
+        src, dst, idx = g[f'src_{k}'], g[f'dst_{k}'], g[f'idx_{k}']
+        pass_t = float(g[f'pass_{k}'])
+        with replay(idx):
+            s_in, d_in, ratio = pf.pose_utils.getRANSACInliers(_hom(src), _hom(dst), MaxIterations=idx.shape[0],
+                                                               PassThreshold=pass_t, StopThreshold=pass_t / 100)
+        np.testing.assert_array_equal(s_in[:3].T, g[f'src_in_{k}'])
+        np.testing.assert_array_equal(d_in[:3].T, g[f'dst_in_{k}'])
+        assert ratio == float(g[f'ratio_{k}'])
+
+
+def test_estimateSimilarityTransform(pf, golden_dir, monkeypatch, capsys):
+    g = np.load(os.path.join(golden_dir, 'ransac.npz'))
+    for k in range(int(g['count'])):
+        name, idx = str(g[f'name_{k}']), g[f'idx_{k}']
+        monkeypatch.setattr(pf.pose_utils, 'N_ITERATIONS', idx.shape[0])
+        with replay(idx):
+            scales, rot, trans, tf = pf.pose_utils.estimateSimilarityTransform(g[f'src_{k}'], g[f'dst_{k}'])
+        if not bool(g[f'ok_{k}']):
+            assert scales is None and rot is None and trans is None and tf is None, name
+            assert 'Small BestInlierRatio' in capsys.readouterr().out
+            continue
+        assert rot_err_deg(rot, g[f'rotation_{k}']) < 1e-6, name
+        np.testing.assert_allclose(scales, g[f'scales_{k}'], rtol=1e-9, err_msg=name)
+        np.testing.assert_allclose(trans, g[f'translation_{k}'], rtol=1e-9, atol=1e-9, err_msg=name)
+
+
+@pytest.mark.parametrize('tag,h,w,b', [('small', 24, 32, 6), ('odd', 19, 27, 4)])
+def test_backproject_transform_cam2world(pf, golden_dir, tag, h, w, b):
+    g = np.load(os.path.join(golden_dir, 'frames.npz'))
+    k_mat = g[f'{tag}_K']
+    for i in range(b):
+        x0, y0 = (int(v) for v in g[f'{tag}_bbox_xy0'][i])
+        depth = np.zeros((240, 320))
+        mask = np.zeros((240, 320), dtype=bool)
+        depth[y0:y0 + h, x0:x0 + w] = g[f'{tag}_depth'][i]
+        mask[y0:y0 + h, x0:x0 + w] = g[f'{tag}_mask'][i] != 0
+        pts, (rows, cols) = pf.pose_estimation.backproject(depth, k_mat, mask)
+        if int(g[f'{tag}_{i}_status']) == 1:
+            assert pts.shape == (0, 3)
+            continue
+        np.testing.assert_array_equal(rows, g[f'{tag}_{i}_rows'])
+        np.testing.assert_array_equal(cols, g[f'{tag}_{i}_cols'])
+        np.testing.assert_allclose(pts, g[f'{tag}_{i}_pts'], rtol=1e-14, atol=1e-14)
+        if int(g[f'{tag}_{i}_status']) == 0:
+            cam = pf.pose_estimation.transform_pc(g[f'{tag}_{i}_ransac_scales'], g[f'{tag}_{i}_ransac_rotation'],
+                                                  g[f'{tag}_{i}_ransac_translation'], g[f'{tag}_{i}_noc_pts'])
+            np.testing.assert_allclose(cam, g[f'{tag}_{i}_transformed_pc'], rtol=1e-12, atol=1e-12)
+            world = pf.pose_estimation.cam2world(cam, g[f'{tag}_{i}_campose'])
+            np.testing.assert_allclose(world, g[f'{tag}_{i}_world_pc'], rtol=1e-12, atol=1e-12)
+
+
+def test_run_pose_against_oracle(pf, monkeypatch):
+    """run_pose end to end (minus the Open3D / GT-clip filters) vs the oracle's restatement of
+    pose_estimation.py:256-290, :323, :359-367, :401-412 with the same replayed indices."""
+    h, w = 48, 56
+    d = pf.synth.make_objects(3, h, w, seed=77, outlier_range=(25.0, 40.0))
+    rng = np.random.default_rng(3)
+    for i in range(3):
+        x0, y0 = (int(v) for v in d['bbox_xy0'][i])
+        depth = rng.uniform(1.0, 5.0, size=(240, 320)).astype(np.float32)      # clutter outside the box is ignored
+        depth[y0:y0 + h, x0:x0 + w] = d['depth'][i].numpy()
+        mask = rng.uniform(size=(240, 320)) < 0.5
+        mask[y0:y0 + h, x0:x0 + w] = d['mask'][i].numpy() != 0
+        noc_hwc = d['noc'][i].permute(1, 2, 0).contiguous()
+        campose = np.identity(4)
+        campose[:3, :3] = np.linalg.qr(rng.normal(size=(3, 3)))[0]
+        campose[:3, 3] = rng.normal(size=3)
+        bbox = (x0, y0, x0 + w, y0 + h)
+        noc_pts, depth_pts, _ = po.crop_correspondences(noc_hwc.numpy(), depth, mask, bbox)
+        idx = rng.integers(0, noc_pts.shape[0], size=(100, 10))
+        ora = po.pose_from_correspondences(noc_pts, depth_pts, idx)
+        with replay(idx):
+            out = pf.pose_estimation.run_pose(noc_hwc.cuda(), depth, campose, torch.from_numpy(mask).cuda(), bbox)
+        assert ora['status'] == 0
+        g_rot, g_trans, g_scale, box, depth_world, world_pc = out
+        want = campose @ po.object_to_camera(np.full(3, ora['s']), ora['rot_t'], ora['t'])
+        np.testing.assert_allclose(g_rot, want[:3, :3], rtol=1e-7, atol=1e-7)
+        np.testing.assert_allclose(g_trans, want[:3, 3], rtol=1e-7, atol=1e-7)
+        np.testing.assert_allclose(g_scale, ora['s'], rtol=1e-9)
+        np.testing.assert_allclose(depth_world, po.camera_to_world(depth_pts, campose), rtol=1e-12, atol=1e-12)
+        cam = po.apply_similarity(np.full(3, ora['s']), ora['rot_t'], ora['t'], noc_pts)
+        np.testing.assert_allclose(world_pc, po.camera_to_world(cam, campose), rtol=1e-6, atol=1e-6)
+        assert box.shape == (8, 3)
+        np.testing.assert_allclose(box.min(0), depth_world.min(0))
+        np.testing.assert_allclose(box.max(0), depth_world.max(0))
+        # office variant: camera space, explicit intrinsics
+        with replay(idx):
+            out2 = pf.pose_estimation.run_pose_office(noc_hwc.cuda(), torch.from_numpy(depth)[None],
+                                                      torch.from_numpy(po.motfront_intrinsics())[None],
+                                                      torch.from_numpy(mask).cuda(), bbox)
+        np.testing.assert_allclose(out2[1], ora['t'], rtol=1e-9)
+        np.testing.assert_allclose(out2[0], ora['s'] * ora['R'], rtol=1e-7, atol=1e-7)
+    # empty mask -> 6 x None (pose_estimation.py:361-362)
+    none = pf.pose_estimation.run_pose(noc_hwc.cuda(), depth, campose, torch.zeros(240, 320, dtype=torch.bool).cuda(), bbox)
+    assert all(v is None for v in none)
