@@ -263,43 +263,49 @@ struct Fit {
 
 enum { PF_OK = 0, PF_EMPTY = 1, PF_LOW_INLIER_RATIO = 2, PF_NAN = 3 };
 
-// Rotation maximising tr(R^T C) over SO(3) plus H and Linv.  PRECISE=true: double Jacobi start
-// (used once per object); false: float start + more Newton steps (used per RANSAC hypothesis),
-// falling back to the double start if the skew residual has not collapsed.
-template <bool PRECISE>
+// Rotation maximising tr(R^T C) over SO(3) plus H (and Linv when WANT_LINV).  PRECISE=true: double
+// Jacobi start + one Newton step (used once per object); false: float start + two Newton steps
+// (used per RANSAC hypothesis).  Newton converges quadratically, so the skew residual measured
+// BEFORE the second step bounds the error after it by its square; if it has not collapsed the
+// hypothesis is redone from a double start.
+template <bool PRECISE, bool WANT_LINV>
 PF_HD void solve_rotation(const double* C, double* R, double* H, double* Linv) {
   double m = 0.0;
 #pragma unroll
   for (int i = 0; i < 9; ++i) m = fmax(m, fabs(C[i]));
   bool nonzero;
   if (PRECISE) nonzero = rotation_start<double, 6>(C, R);
-  else nonzero = rotation_start<float, 4>(C, R);
+  else nonzero = rotation_start<float, 3>(C, R);
 #pragma unroll
-  for (int i = 0; i < 6; ++i) { H[i] = 0.0; Linv[i] = 0.0; }
+  for (int i = 0; i < 6; ++i) { H[i] = 0.0; if (WANT_LINV) Linv[i] = 0.0; }
   if (!nonzero) return;
   double Cn[9];
   const double inv = 1.0 / m;
 #pragma unroll
   for (int i = 0; i < 9; ++i) Cn[i] = C[i] * inv;
-  if (!PRECISE) {
+  if (PRECISE) {
+    newton_step(Cn, R);
+  } else {
     orthonormalize_step(R);
     newton_step(Cn, R);
-    newton_step(Cn, R);
-    const double kn = newton_step(Cn, R);     // residual BEFORE the third step
-    if (!(kn < 1e-7)) {                       // not in the quadratic regime: redo from a double start
+    const double kn = newton_step(Cn, R);     // residual BEFORE the second step
+    if (!(kn < 1e-8)) {                       // not in the quadratic regime: redo from a double start
       rotation_start<double, 6>(C, R);
       newton_step(Cn, R);
     }
   }
-  newton_step(Cn, R);
   orthonormalize_step(R);
   double M[9];
   rt_times(R, Cn, M);
   double Hn[6] = {M[0], 0.5 * (M[1] + M[3]), 0.5 * (M[2] + M[6]), M[4], 0.5 * (M[5] + M[7]), M[8]};
-  double Li[6] = {0, 0, 0, 0, 0, 0};
-  inv_trace_minus(Hn, Li);
 #pragma unroll
-  for (int i = 0; i < 6; ++i) { H[i] = Hn[i] * m; Linv[i] = Li[i] * inv; }
+  for (int i = 0; i < 6; ++i) H[i] = Hn[i] * m;
+  if (WANT_LINV) {
+    double Li[6] = {0, 0, 0, 0, 0, 0};
+    inv_trace_minus(Hn, Li);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) Linv[i] = Li[i] * inv;
+  }
 }
 
 // ox / oy (optional): origin the sums were shifted by (x - ox, y - oy were accumulated); C and
@@ -330,7 +336,7 @@ PF_HD void fit_from_moments(const Moments& mo, Fit& f, const double* ox = nullpt
     }
   if (nan) { f.status = PF_NAN; return; }
   f.var = mo.sxx * rn - (f.mux[0] * f.mux[0] + f.mux[1] * f.mux[1] + f.mux[2] * f.mux[2]);
-  solve_rotation<PRECISE>(C, f.R, f.H, f.Linv);
+  solve_rotation<PRECISE, PRECISE>(C, f.R, f.H, f.Linv);   // hypotheses never need Linv
   if (ox != nullptr) {
 #pragma unroll
     for (int i = 0; i < 3; ++i) { f.mux[i] += ox[i]; f.muy[i] += oy[i]; }

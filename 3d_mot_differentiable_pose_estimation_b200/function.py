@@ -43,9 +43,9 @@ def _stream(device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
 
-def _workspace(lib, dev, b: int, h: int, w: int) -> torch.Tensor:
-    """Caller-owned scratch for the plain fit (partial moments), sized by the library."""
-    nbytes = int(lib.posefit_workspace_bytes(b, h, w, 0, 0))
+def _workspace(lib, dev, b: int, h: int, w: int, n_hyp: int = 0, n_samp: int = 0) -> torch.Tensor:
+    """Caller-owned scratch (partial moments / per-object records), sized by the library."""
+    nbytes = int(lib.posefit_workspace_bytes(b, h, w, n_hyp, n_samp))
     return torch.empty(max(nbytes, 8), dtype=torch.uint8, device=dev)
 
 
@@ -112,10 +112,11 @@ def pose_fit_raw(noc, depth, mask, bbox_xy0, kinv=None, sample_idx=None, ratio_a
         n_hyp, n_samp = int(sample_idx.shape[1]), int(sample_idx.shape[2])
         inl = torch.empty(b, h, w, dtype=torch.uint8, device=dev)
         winner = torch.empty(b, dtype=torch.int32, device=dev)
+        ws = _workspace(lib, dev, b, h, w, max(n_hyp, 1), n_samp)
         code = lib.posefit_forward_ransac(_ptr(noc), _ptr(depth), _ptr(mask), _ptr(bbox_xy0), _ptr(kinv), per_obj,
                                           _ptr(sample_idx), b, h, w, n_hyp, n_samp, float(ratio_adapt),
                                           int(bool(ref_compat)), _ptr(pose), _ptr(ctx), _ptr(status), _ptr(n_valid),
-                                          _ptr(inl), _ptr(winner), None, 0, _stream(dev))
+                                          _ptr(inl), _ptr(winner), _ptr(ws), ws.numel(), _stream(dev))
         _lib.check(code, 'posefit_forward_ransac')
     return PoseFitRaw(pose, ctx, status, n_valid, inl, winner)
 
@@ -151,11 +152,12 @@ def points_fit_raw(src, dst, mask=None, sample_idx=None, ratio_adapt: float = 1.
         n_hyp, n_samp = int(sample_idx.shape[1]), int(sample_idx.shape[2])
         inl = torch.empty(b, n, dtype=torch.uint8, device=dev)
         winner = torch.empty(b, dtype=torch.int32, device=dev)
+        ws = _workspace(lib, dev, b, 1, n, max(n_hyp, 1), n_samp)
         code = lib.posefit_points_forward_ransac(_ptr(src), _ptr(dst), _ptr(mask), _ptr(sample_idx), b, n, n_hyp,
                                                  n_samp, float(ratio_adapt), float(pass_threshold),
                                                  float(stop_threshold), int(bool(ref_compat)), _ptr(pose),
                                                  _ptr(ctx), _ptr(status), _ptr(n_valid), _ptr(inl), _ptr(winner),
-                                                 None, 0, _stream(dev))
+                                                 _ptr(ws), ws.numel(), _stream(dev))
         _lib.check(code, 'posefit_points_forward_ransac')
     return PoseFitRaw(pose, ctx, status, n_valid, inl, winner)
 
