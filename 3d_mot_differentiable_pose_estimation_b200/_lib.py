@@ -21,7 +21,7 @@ ABI_VERSION = 1
 
 # every symbol include/posefit.h declares
 SYMBOLS = ('posefit_version', 'posefit_error_string', 'posefit_workspace_bytes', 'posefit_forward',
-           'posefit_forward_ransac', 'posefit_backward', 'posefit_launch_count',
+           'posefit_forward_ransac', 'posefit_backward', 'posefit_backward_workspace_bytes', 'posefit_launch_count',
            'posefit_points_forward', 'posefit_points_forward_ransac', 'posefit_compact',
            'posefit_points_evaluate', 'posefit_transform_points')
 
@@ -67,7 +67,9 @@ def _declare(lib):
     lib.posefit_forward_ransac.argtypes = [vp, vp, vp, vp, vp, i32, vp, i32, i32, i32, i32, i32, f64, i32,
                                            vp, vp, vp, vp, vp, vp, vp, sz, vp]
     lib.posefit_backward.restype = i32
-    lib.posefit_backward.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.posefit_backward.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]
+    lib.posefit_backward_workspace_bytes.restype = sz
+    lib.posefit_backward_workspace_bytes.argtypes = [i32]
     lib.posefit_points_forward.restype = i32
     lib.posefit_points_forward.argtypes = [vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, sz, vp]
     lib.posefit_points_forward_ransac.restype = i32

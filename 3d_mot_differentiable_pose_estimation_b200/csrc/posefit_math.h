@@ -263,19 +263,18 @@ struct Fit {
 
 enum { PF_OK = 0, PF_EMPTY = 1, PF_LOW_INLIER_RATIO = 2, PF_NAN = 3 };
 
-// Rotation maximising tr(R^T C) over SO(3) plus H (and Linv when WANT_LINV).  PRECISE=true: double
-// Jacobi start + one Newton step (used once per object); false: float start + two Newton steps
-// (used per RANSAC hypothesis).  Newton converges quadratically, so the skew residual measured
-// BEFORE the second step bounds the error after it by its square; if it has not collapsed the
-// hypothesis is redone from a double start.
-template <bool PRECISE, bool WANT_LINV>
+// Rotation maximising tr(R^T C) over SO(3) plus H (and Linv when WANT_LINV).
+// Start: one-sided Jacobi in float (3 sweeps, ~1e-6), one Newton-Schulz orthonormalisation, then
+// Newton steps on SO(3) in double.  Newton converges quadratically, so the skew residual measured
+// BEFORE a step bounds the error after it by its square; if it has not collapsed before the
+// second step the solve is redone from a double-precision Jacobi start (near-degenerate C only).
+// EXTRA_STEP adds a third Newton step (used for the once-per-object fits; hypotheses skip it).
+template <bool EXTRA_STEP, bool WANT_LINV>
 PF_HD void solve_rotation(const double* C, double* R, double* H, double* Linv) {
   double m = 0.0;
 #pragma unroll
   for (int i = 0; i < 9; ++i) m = fmax(m, fabs(C[i]));
-  bool nonzero;
-  if (PRECISE) nonzero = rotation_start<double, 6>(C, R);
-  else nonzero = rotation_start<float, 3>(C, R);
+  const bool nonzero = rotation_start<float, 3>(C, R);
 #pragma unroll
   for (int i = 0; i < 6; ++i) { H[i] = 0.0; if (WANT_LINV) Linv[i] = 0.0; }
   if (!nonzero) return;
@@ -283,17 +282,15 @@ PF_HD void solve_rotation(const double* C, double* R, double* H, double* Linv) {
   const double inv = 1.0 / m;
 #pragma unroll
   for (int i = 0; i < 9; ++i) Cn[i] = C[i] * inv;
-  if (PRECISE) {
+  orthonormalize_step(R);
+  newton_step(Cn, R);
+  const double kn = newton_step(Cn, R);       // residual BEFORE the second step
+  if (!(kn < 1e-8)) {                         // not in the quadratic regime: redo from a double start
+    rotation_start<double, 6>(C, R);
     newton_step(Cn, R);
-  } else {
-    orthonormalize_step(R);
     newton_step(Cn, R);
-    const double kn = newton_step(Cn, R);     // residual BEFORE the second step
-    if (!(kn < 1e-8)) {                       // not in the quadratic regime: redo from a double start
-      rotation_start<double, 6>(C, R);
-      newton_step(Cn, R);
-    }
   }
+  if (EXTRA_STEP) newton_step(Cn, R);
   orthonormalize_step(R);
   double M[9];
   rt_times(R, Cn, M);

@@ -180,10 +180,11 @@ def pose_fit_backward_raw(noc, depth, mask, inlier_mask, bbox_xy0, kinv, ctx, st
     g_depth = torch.empty_like(depth) if want_depth_grad else None
     if inlier_mask is not None:
         inlier_mask = inlier_mask.to(torch.uint8).contiguous()
+    ws = torch.empty(max(int(lib.posefit_backward_workspace_bytes(b)), 16), dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
         code = lib.posefit_backward(_ptr(noc), _ptr(depth), _ptr(mask), _ptr(inlier_mask), _ptr(bbox_xy0), _ptr(kinv),
                                     per_obj, b, h, w, _ptr(ctx), _ptr(status), _ptr(grad_scale), _ptr(grad_R),
-                                    _ptr(grad_t), _ptr(g_noc), _ptr(g_depth), _stream(dev))
+                                    _ptr(grad_t), _ptr(g_noc), _ptr(g_depth), _ptr(ws), ws.numel(), _stream(dev))
     _lib.check(code, 'posefit_backward')
     return g_noc, g_depth
 

@@ -127,7 +127,11 @@ int posefit_backward(const float* noc, const float* depth, const uint8_t* mask, 
                      int n_objects, int height, int width,
                      const double* ctx, const int32_t* status,
                      const float* grad_scale, const float* grad_R, const float* grad_t,
-                     float* grad_noc, float* grad_depth, void* stream);
+                     float* grad_noc, float* grad_depth,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* Bytes of device scratch posefit_backward needs (per-object adjoint coefficients, 16-byte aligned). */
+size_t posefit_backward_workspace_bytes(int n_objects);
 
 /* Stable row-major compaction of every crop: the correspondences exactly as the reference builds
  * them before the fit -- `backproject` (PoseEst/pose_estimation.py:16-43: points and the np.where
