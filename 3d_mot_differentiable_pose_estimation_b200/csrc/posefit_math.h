@@ -333,6 +333,13 @@ PF_HD void fit_from_moments(const Moments& mo, Fit& f, const double* ox = nullpt
     }
   if (nan) { f.status = PF_NAN; return; }
   f.var = mo.sxx * rn - (f.mux[0] * f.mux[0] + f.mux[1] * f.mux[1] + f.mux[2] * f.mux[2]);
+  if (mo.n == 1.0) {
+    // a single correspondence: the centred cloud is exactly zero in the reference (U = Vh = I, s = 1,
+    // pose_utils.py:27-50); uncentred sums only reach that up to rounding, so say it explicitly
+#pragma unroll
+    for (int i = 0; i < 9; ++i) C[i] = 0.0;
+    f.var = 0.0;
+  }
   solve_rotation<PRECISE, PRECISE>(C, f.R, f.H, f.Linv);   // hypotheses never need Linv
   if (ox != nullptr) {
 #pragma unroll
