@@ -136,6 +136,19 @@ def test_tma_and_fallback_loaders_agree(pf, monkeypatch):
     assert torch.equal(ar.inlier_mask, br.inlier_mask)
 
 
+def test_ransac_fast_and_generic_passes_agree(pf, monkeypatch):
+    d = pf.synth.make_objects(64, 64, 64, seed=22, n_hyp=128)
+    t = _cuda(d)
+    a = pf.pose_fit_raw(t['noc'], t['depth'], t['mask'], t['bbox_xy0'], sample_idx=t['sample_idx'])
+    monkeypatch.setenv('POSEFIT_NO_FAST', '1')
+    b = pf.pose_fit_raw(t['noc'], t['depth'], t['mask'], t['bbox_xy0'], sample_idx=t['sample_idx'])
+    torch.cuda.synchronize()
+    assert torch.equal(a.inlier_mask, b.inlier_mask) and torch.equal(a.winner, b.winner)
+    assert torch.equal(a.status, b.status)
+    assert float((a.pose[:, :13] - b.pose[:, :13]).abs().max()) < 1e-10
+    assert float((a.pose[:, 15] - b.pose[:, 15]).abs().max() / b.pose[:, 15].abs().max()) < 1e-6
+
+
 def test_edge_cases(pf):
     d = pf.synth.make_objects(6, 64, 64, seed=31, n_hyp=16)
     d['mask'][0] = 0                                  # empty -> status 1 (pose_estimation.py:361-362)
