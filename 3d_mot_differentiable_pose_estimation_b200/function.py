@@ -189,6 +189,44 @@ def pose_fit_backward_raw(noc, depth, mask, inlier_mask, bbox_xy0, kinv, ctx, st
     return g_noc, g_depth
 
 
+class PoseEpilogue(NamedTuple):
+    global_rot: torch.Tensor     # [B,3,3] f64, scale embedded (pose_estimation.py:404-406)
+    global_trans: torch.Tensor   # [B,3]
+    global_scale: torch.Tensor   # [B]
+    euler: torch.Tensor          # [B,3] XYZ Euler angles of the unscaled rotation (postprocess.py:158-160)
+    world_box: torch.Tensor      # [B,8,3] sort_bbox-ordered world box of the depth points (:373-380)
+
+
+def pose_epilogue(raw: PoseFitRaw, depth, mask, bbox_xy0, kinv=None, campose=None, cam_index=None) -> PoseEpilogue:
+    """Batched tail of run_pose on the GPU (no per-instance Python loop, no host round trips).
+    campose: [4,4], [F,4,4] with cam_index[B], or [B,4,4] camera-to-world matrices; None keeps camera
+    space (run_pose_office)."""
+    lib = _lib.lib()
+    dev = raw.pose.device
+    b = int(raw.pose.shape[0])
+    depth = depth.detach().to(device=dev, dtype=torch.float32).contiguous()
+    h, w = int(depth.shape[1]), int(depth.shape[2])
+    mask = mask.to(device=dev, dtype=torch.uint8).contiguous()
+    bbox_xy0 = bbox_xy0.to(device=dev, dtype=torch.int32).contiguous()
+    kinv, per_obj = _prep_kinv(kinv, dev, b)
+    n_cam = 0
+    if campose is not None:
+        campose = torch.as_tensor(campose).to(device=dev, dtype=torch.float64).reshape(-1, 16).contiguous()
+        n_cam = int(campose.shape[0])
+    if cam_index is not None:
+        cam_index = cam_index.to(device=dev, dtype=torch.int32).contiguous()
+    elif n_cam not in (0, 1, b):
+        raise ValueError('campose must be [4,4] or [B,4,4] unless cam_index is given')
+    out = torch.empty(b, 40, dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        code = lib.posefit_epilogue(_ptr(depth), _ptr(mask), _ptr(bbox_xy0), _ptr(kinv), per_obj, _ptr(raw.pose),
+                                    _ptr(raw.status), _ptr(campose), n_cam, _ptr(cam_index), b, h, w, _ptr(out),
+                                    _stream(dev))
+    _lib.check(code, 'posefit_epilogue')
+    return PoseEpilogue(out[:, 0:9].reshape(b, 3, 3), out[:, 9:12], out[:, 12], out[:, 13:16],
+                        out[:, 16:40].reshape(b, 8, 3))
+
+
 class PoseFit(torch.autograd.Function):
     """(scale[B], R[B,3,3], t[B,3], inlier_mask[B,H,W] u8, status[B] i32, n_valid[B] i32) =
     PoseFit.apply(noc, depth, mask, bbox_xy0, kinv, sample_idx, ratio_adapt, ref_compat).

@@ -104,12 +104,37 @@ def cpu_objects_per_s(sample, with_bwd=True, ransac=False, procs=None):
     return n / dt, len(jobs)
 
 
+def cpu_model():
+    try:
+        for line in open('/proc/cpuinfo'):
+            if line.startswith('model name'):
+                return line.split(':', 1)[1].strip()
+    except OSError:
+        pass
+    return 'unknown'
+
+
+def _subsample(sample, n):
+    return {k: v[:n] for k, v in sample.items()}
+
+
 def cpu_baseline(pf, size, n_sample, kind='port'):
-    sample = pf.synth.make_objects(n_sample, size, size, seed=9001)
+    """Headline baseline: fwd+bwd on all host cores; plus one core, and the forward-only / RANSAC
+    variants of configs 2 and 3 (each a bounded sample, stated)."""
+    sample = pf.synth.make_objects(n_sample, size, size, seed=9001, n_hyp=128)
     value, cores = cpu_objects_per_s(sample, with_bwd=True)
-    return {'value': value, 'unit': UNIT, 'cores': cores, 'kind': kind,
+    n1 = max(8, n_sample // max(cores, 1))
+    one, _ = cpu_objects_per_s(_subsample(sample, n1), with_bwd=True, procs=1)
+    fwd, _ = cpu_objects_per_s(sample, with_bwd=False)
+    n_r = max(cores, min(n_sample, 8 * cores))
+    rans, _ = cpu_objects_per_s(_subsample(sample, n_r), with_bwd=False, ransac=True)
+    return {'value': value, 'unit': UNIT, 'cores': cores, 'kind': kind, 'cpu_model': cpu_model(),
+            'single_core_value': one,
+            'config2_fwd_plain_value': fwd, 'config3_ransac128_value': rans,
             'sample': f'{n_sample} objects of the same {size}x{size} workload, fwd (NumPy restatement of '
-                      f'backproject+Umeyama) + bwd (fp64 torch-autograd restatement), {cores} processes x 1 thread'}
+                      f'backproject+Umeyama, fp64) + bwd (fp64 torch-autograd restatement), {cores} processes x 1 '
+                      f'thread; single core on {n1} objects; config 2 (fwd only) on {n_sample}, config 3 '
+                      f'(RANSAC 128 hyp, replayed indices) on {n_r} objects'}
 
 
 # ----------------------------------------------------------------------------------------------
@@ -219,7 +244,7 @@ def run_ours(args):
         e2.record()
         if world > 1:
             pf.shard.gather_poses(raw.pose)                      # the one collective: final gather of poses
-        return [('fit_stream_kernel', e0, e1), ('fit_backward_kernel', e1, e2)]
+        return [('fit_moments_kernel', e0, e1), ('fit_backward_kernel', e1, e2)]
 
     for _ in range(args.warmup):
         step()
@@ -254,14 +279,28 @@ def run_ours(args):
     bytes_fwd = n_obj * (17 * P + 64)
     bytes_bwd = n_obj * (29 * P + 52)
     kernels = {
-        'fit_stream_kernel': {'ms': kern['fit_stream_kernel'], 'algorithmic_bytes': bytes_fwd,
-                              'gbs': bytes_fwd / kern['fit_stream_kernel'] / 1e6},
+        'fit_moments_kernel': {'ms': kern['fit_moments_kernel'], 'algorithmic_bytes': bytes_fwd,
+                               'gbs': bytes_fwd / kern['fit_moments_kernel'] / 1e6,
+                               'note': 'interval also contains the dependent fit_solve_kernel (3x3 solves)'},
         'fit_backward_kernel': {'ms': kern['fit_backward_kernel'], 'algorithmic_bytes': bytes_bwd,
-                                'gbs': bytes_bwd / kern['fit_backward_kernel'] / 1e6},
+                                'gbs': bytes_bwd / kern['fit_backward_kernel'] / 1e6,
+                                'note': 'interval also contains fit_backward_coef_kernel (per-object adjoint)'},
     }
+    traffic = {}
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')) as f:
+            tj = json.load(f)
+        for kname in kernels:
+            if kname in tj and size == 64:
+                traffic[kname] = tj[kname]['bytes_per_object'] * n_obj
+                kernels[kname]['traffic'] = traffic[kname]
+    except (OSError, ValueError):
+        pass
     dom = max(kernels, key=lambda k: kernels[k]['ms'])
     roofline = {'bound': 'hbm', 'kernel': dom, 'achieved': kernels[dom]['gbs'], 'peak': hbm_peak, 'unit': 'GB/s',
-                'frac': kernels[dom]['gbs'] / hbm_peak, 'traffic': None, 'peak_source': peak_src,
+                'frac': kernels[dom]['gbs'] / hbm_peak, 'traffic': traffic.get(dom),
+                'traffic_source': 'ncu --set full dram bytes per object (profiles/ncu_traffic.json) x objects per launch',
+                'peak_source': peak_src,
                 'step_achieved': (bytes_fwd + bytes_bwd) / ms / 1e6,
                 'step_frac': (bytes_fwd + bytes_bwd) / ms / 1e6 / hbm_peak, 'kernels': kernels}
 

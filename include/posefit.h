@@ -156,6 +156,22 @@ int posefit_points_evaluate(const double* transform, const double* src, const do
 int posefit_transform_points(const double* matrix, int matrix_per_object, const double* points, double* out,
                              int n_objects, int n_points, void* stream);
 
+/* Batched tail of run_pose (PoseEst/pose_estimation.py:367-412) plus the Euler conversion of its
+ * callers (Detection/tracker/postprocess.py:158-160): for every object
+ *   out[b][0..8]   global_rot  = (campose @ [s R | t])[:3,:3]   (scale embedded, :404-406)
+ *   out[b][9..11]  global_trans
+ *   out[b][12]     global_scale = s
+ *   out[b][13..15] XYZ Euler angles of global_rot / column norms (get_scale + mathutils to_euler)
+ *   out[b][16..39] world-space axis-aligned box of the object's depth points, 8 corners in the
+ *                  reference's sort_bbox order (:72-93, :373-380); zeros when status != 0.
+ * campose: n_campose row-major 4x4 camera-to-world matrices; cam_index[b] picks one per object
+ * (NULL: n_campose == 1 -> shared, else one per object); campose == NULL keeps camera space
+ * (run_pose_office, :501-512). */
+int posefit_epilogue(const float* depth, const uint8_t* mask, const int32_t* bbox_xy0, const double* kinv,
+                     int kinv_per_object, const double* pose, const int32_t* status, const double* campose,
+                     int n_campose, const int32_t* cam_index, int n_objects, int height, int width, double* out,
+                     void* stream);
+
 /* Number of kernels this library has launched in the calling process (for bench.py's
  * gpu_launches claim). */
 unsigned long long posefit_launch_count(void);

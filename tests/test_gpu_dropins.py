@@ -168,3 +168,60 @@ def test_run_pose_against_oracle(pf, monkeypatch):
     # empty mask -> 6 x None (pose_estimation.py:361-362)
     none = pf.pose_estimation.run_pose(noc_hwc.cuda(), depth, campose, torch.zeros(240, 320, dtype=torch.bool).cuda(), bbox)
     assert all(v is None for v in none)
+
+
+def _euler_xyz_blender(m):
+    """mathutils.Matrix(m).to_euler() ('XYZ'), restated from Blender's mat3_normalized_to_eul2
+    (mathutils 2.81.2 is not installed: unpinned)."""
+    cy = np.hypot(m[0, 0], m[1, 0])
+    if cy > 16 * 1.1920929e-07:
+        e1 = np.array([np.arctan2(m[2, 1], m[2, 2]), np.arctan2(-m[2, 0], cy), np.arctan2(m[1, 0], m[0, 0])])
+        e2 = np.array([np.arctan2(-m[2, 1], -m[2, 2]), np.arctan2(-m[2, 0], -cy), np.arctan2(-m[1, 0], -m[0, 0])])
+    else:
+        e1 = np.array([np.arctan2(-m[1, 2], m[1, 1]), np.arctan2(-m[2, 0], cy), 0.0])
+        e2 = e1
+    return e2 if np.abs(e1).sum() > np.abs(e2).sum() else e1
+
+
+def test_batched_epilogue(pf):
+    """posefit_epilogue == the per-object tail of run_pose (pose_estimation.py:367-412) + the Euler
+    conversion of postprocess.py:158-160, for a batch with per-frame camera poses."""
+    b, h, w, frames = 24, 40, 48, 3
+    d = pf.synth.make_objects(b, h, w, seed=91)
+    d['mask'][5] = 0                                       # one empty object
+    rng = np.random.default_rng(9)
+    campose = np.tile(np.identity(4), (frames, 1, 1))
+    for f in range(frames):
+        campose[f, :3, :3] = np.linalg.qr(rng.normal(size=(3, 3)))[0]
+        campose[f, :3, 3] = rng.normal(size=3)
+    cam_index = np.arange(b) % frames
+    t = {k: d[k].cuda() for k in ('noc', 'depth', 'mask', 'bbox_xy0')}
+    raw = pf.pose_fit_raw(t['noc'], t['depth'], t['mask'], t['bbox_xy0'])
+    epi = pf.pose_epilogue(raw, t['depth'], t['mask'], t['bbox_xy0'], campose=torch.from_numpy(campose),
+                           cam_index=torch.from_numpy(cam_index))
+    ora = po.batch_pose(d['noc'].numpy(), d['depth'].numpy(), d['mask'].numpy(), d['bbox_xy0'].numpy())
+    for i, o in enumerate(ora):
+        if o['status'] != 0:
+            assert float(epi.world_box[i].abs().max()) == 0.0
+            continue
+        cp = campose[cam_index[i]]
+        want = cp @ po.object_to_camera(np.full(3, o['s']), o['rot_t'], o['t'])
+        np.testing.assert_allclose(epi.global_rot[i].cpu().numpy(), want[:3, :3], rtol=1e-9, atol=1e-9)
+        np.testing.assert_allclose(epi.global_trans[i].cpu().numpy(), want[:3, 3], rtol=1e-9, atol=1e-9)
+        np.testing.assert_allclose(float(epi.global_scale[i]), o['s'], rtol=1e-10)
+        unscaled = want[:3, :3] / np.linalg.norm(want[:3, :3], axis=0)
+        np.testing.assert_allclose(epi.euler[i].cpu().numpy(), _euler_xyz_blender(unscaled), rtol=1e-8, atol=1e-8)
+        x0, y0 = (int(v) for v in d['bbox_xy0'][i])
+        fd = np.zeros((240, 320), dtype=np.float32)
+        fm = np.zeros((240, 320), dtype=bool)
+        fd[y0:y0 + h, x0:x0 + w] = d['depth'][i].numpy()
+        fm[y0:y0 + h, x0:x0 + w] = d['mask'][i].numpy() != 0
+        pts, _ = po.backproject_points(fd.astype(np.float64), po.motfront_intrinsics(), fm)
+        world = po.camera_to_world(pts, cp)
+        box = pf.pose_estimation.sort_bbox(pf.pose_estimation._aabb_corners(world))
+        np.testing.assert_allclose(epi.world_box[i].cpu().numpy(), box, rtol=1e-12, atol=1e-12)
+    # camera-space variant (run_pose_office)
+    epi2 = pf.pose_epilogue(raw, t['depth'], t['mask'], t['bbox_xy0'])
+    i = 0
+    np.testing.assert_allclose(epi2.global_rot[i].cpu().numpy(), ora[i]['s'] * ora[i]['R'], rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(epi2.global_trans[i].cpu().numpy(), ora[i]['t'], rtol=1e-10)
