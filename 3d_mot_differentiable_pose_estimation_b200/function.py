@@ -227,6 +227,36 @@ def pose_epilogue(raw: PoseFitRaw, depth, mask, bbox_xy0, kinv=None, campose=Non
                         out[:, 16:40].reshape(b, 8, 3))
 
 
+def clip_mask_to_box(depth, mask, bbox_xy0, gt_box, campose, kinv=None, cam_index=None, min_keep: int = 20):
+    """GT-box pre-filter of run_pose (clean_depth, pose_estimation.py:107-134, :293-299) as a mask:
+    returns (new_mask [B,H,W] u8, kept [B] i32).  gt_box [B,8,3]; campose [4,4], [B,4,4] or [F,4,4] +
+    cam_index[B]."""
+    lib = _lib.lib()
+    if not depth.is_cuda:
+        raise _lib.PoseFitError('clip_mask_to_box needs CUDA tensors: the solver has no CPU path')
+    dev = depth.device
+    b, h, w = (int(v) for v in depth.shape)
+    depth = depth.detach().to(torch.float32).contiguous()
+    mask = mask.to(device=dev, dtype=torch.uint8).contiguous()
+    bbox_xy0 = bbox_xy0.to(device=dev, dtype=torch.int32).contiguous()
+    kinv, per_obj = _prep_kinv(kinv, dev, b)
+    gt_box = torch.as_tensor(gt_box).to(device=dev, dtype=torch.float64).reshape(b, 24).contiguous()
+    campose = torch.as_tensor(campose).to(device=dev, dtype=torch.float64).reshape(-1, 16).contiguous()
+    n_cam = int(campose.shape[0])
+    if cam_index is not None:
+        cam_index = cam_index.to(device=dev, dtype=torch.int32).contiguous()
+    elif n_cam not in (1, b):
+        raise ValueError('campose must be [4,4] or [B,4,4] unless cam_index is given')
+    out = torch.empty_like(mask)
+    kept = torch.empty(b, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        code = lib.posefit_clip_mask(_ptr(depth), _ptr(mask), _ptr(bbox_xy0), _ptr(kinv), per_obj, _ptr(campose), n_cam,
+                                     _ptr(cam_index), _ptr(gt_box), int(min_keep), b, h, w, _ptr(out), _ptr(kept),
+                                     _stream(dev))
+    _lib.check(code, 'posefit_clip_mask')
+    return out, kept
+
+
 class PoseFit(torch.autograd.Function):
     """(scale[B], R[B,3,3], t[B,3], inlier_mask[B,H,W] u8, status[B] i32, n_valid[B] i32) =
     PoseFit.apply(noc, depth, mask, bbox_xy0, kinv, sample_idx, ratio_adapt, ref_compat).

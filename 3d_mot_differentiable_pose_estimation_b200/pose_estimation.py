@@ -3,9 +3,8 @@
 signatures and return types, computed by the CUDA library.
 
 Not reproduced (third-party, unpinned -- see DESIGN.md section 7): the Open3D
-`remove_statistical_outlier` passes (pose_estimation.py:311-318, :341-349) and the GT-box clip
-`clean_depth` (:293-299).  `run_pose` therefore fits on all `mask & depth>0` correspondences, which
-is what BASELINE.json's configs measure.  The world box is the axis-aligned box of the depth
+`remove_statistical_outlier` passes (pose_estimation.py:311-318, :341-349).  The GT-box clip
+`clean_depth` (:107-134, :293-299) IS reproduced (posefit_clip_mask) when `gt_3d_box` is given.  The world box is the axis-aligned box of the depth
 points in Open3D's corner order followed by the reference's own `sort_bbox`.
 """
 from __future__ import annotations
@@ -14,7 +13,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .function import pose_fit_raw, default_kinv, _ptr, _stream
+from .function import pose_fit_raw, default_kinv, clip_mask_to_box, _ptr, _stream
 
 __all__ = ['backproject', 'transform_pc', 'cam2world', 'sort_bbox', 'run_pose', 'run_pose_office']
 
@@ -112,7 +111,7 @@ def _aabb_corners(pts: np.ndarray) -> np.ndarray:
                      hi, hi - [e[0], 0, 0], hi - [0, e[1], 0], hi - [0, 0, e[2]]])
 
 
-def _run(nocs, depth, kinv, campose, bin_mask, abs_bbox, use_depth_box):
+def _run(nocs, depth, kinv, campose, bin_mask, abs_bbox, use_depth_box, gt_3d_box=None):
     dev = _device()
     x0, y0, x1, y1 = (int(v) for v in _np(abs_bbox).reshape(-1)[:4])
     h, w = y1 - y0, x1 - x0
@@ -126,6 +125,9 @@ def _run(nocs, depth, kinv, campose, bin_mask, abs_bbox, use_depth_box):
     m = (m_full[y0:y1, x0:x1] != 0).to(torch.uint8).contiguous()[None]
     xy0 = torch.tensor([[x0, y0]], dtype=torch.int32, device=dev)
     kinv = kinv.to(dev)
+    if gt_3d_box is not None and campose is not None:                   # clean_depth, :293-299
+        m, _ = clip_mask_to_box(d, m, xy0, torch.as_tensor(_np(gt_3d_box)).reshape(1, 8, 3),
+                                torch.as_tensor(_np(campose)), kinv)
     src, dst, rows, cols = _compact(noc[0], d[0], m[0], xy0, kinv)
     n = int(dst.shape[0])
     if n == 0:                                                          # :361-362
@@ -162,8 +164,9 @@ def _run(nocs, depth, kinv, campose, bin_mask, abs_bbox, use_depth_box):
 
 def run_pose(nocs, depth, campose, bin_mask, abs_bbox, vis_obj=False, gt_pc=None, gt_3d_box=None, use_depth_box=True):
     """pose_estimation.py:245-412 -> (global_rot, global_trans, global_scale, world_box, depth_world,
-    world_pc) or 6 x None.  vis_obj / gt_pc (visualisation) and gt_3d_box (GT clip) are accepted and ignored."""
-    return _run(nocs, depth, default_kinv(), campose, bin_mask, abs_bbox, use_depth_box)
+    world_pc) or 6 x None.  gt_3d_box (8x3, world space) applies the reference's clean_depth clip
+    (:107-134, :293-299); vis_obj / gt_pc (visualisation) are accepted and ignored."""
+    return _run(nocs, depth, default_kinv(), campose, bin_mask, abs_bbox, use_depth_box, gt_3d_box)
 
 
 def run_pose_office(nocs, depth, cam_intrinsics, bin_mask, abs_bbox, vis_obj=False, gt_pc=None, gt_3d_box=None,

@@ -172,6 +172,17 @@ int posefit_epilogue(const float* depth, const uint8_t* mask, const int32_t* bbo
                      int n_campose, const int32_t* cam_index, int n_objects, int height, int width, double* out,
                      void* stream);
 
+/* GT-box pre-filter of run_pose: clean_depth (PoseEst/pose_estimation.py:107-134) applied as at
+ * :293-299.  out_mask[b] = mask & depth>0 & (world-space depth point strictly inside the axis-aligned
+ * extent of gt_box[b] (8x3 float64 corners)) when more than min_keep (reference: 20) points survive,
+ * else the unclipped validity mask.  campose / cam_index as for posefit_epilogue (campose required).
+ * kept[b] (optional) receives the number of surviving correspondences.  Feed out_mask to the fit
+ * entries in place of mask. */
+int posefit_clip_mask(const float* depth, const uint8_t* mask, const int32_t* bbox_xy0, const double* kinv,
+                      int kinv_per_object, const double* campose, int n_campose, const int32_t* cam_index,
+                      const double* gt_box, int min_keep, int n_objects, int height, int width,
+                      uint8_t* out_mask, int32_t* kept, void* stream);
+
 /* Number of kernels this library has launched in the calling process (for bench.py's
  * gpu_launches claim). */
 unsigned long long posefit_launch_count(void);

@@ -226,6 +226,29 @@ def frame_cases(pu, pe):
     return out
 
 
+def clip_cases(pe, rng):
+    """clean_depth (pose_estimation.py:107-134) on random clouds / boxes / camera poses."""
+    out = {}
+    k = 0
+    for n, frac in ((300, 0.6), (1200, 0.3), (50, 0.05), (5, 1.0)):
+        pts = rng.normal(size=(n, 3)) * np.array([0.5, 0.4, 0.6]) + np.array([0.2, -0.1, -3.5])
+        campose = np.identity(4)
+        campose[:3, :3] = _rand_rot(rng)
+        campose[:3, 3] = rng.normal(size=3)
+        world = pe.cam2world(pts, campose)
+        c, e = np.median(world, axis=0), world.std(axis=0) * (0.3 + 2.0 * frac)
+        corners = np.array([[sx, sy, sz] for sx in (-1, 1) for sy in (-1, 1) for sz in (-1, 1)], dtype=np.float64)
+        box = c + corners * e
+        box = box[rng.permutation(8)]
+        new_depth, used = pe.clean_depth(pts, box, campose)
+        out[f'pts_{k}'], out[f'box_{k}'], out[f'campose_{k}'] = pts, box, campose
+        out[f'used_{k}'] = np.asarray(used, dtype=np.int64)
+        out[f'new_depth_{k}'] = np.asarray(new_depth, dtype=np.float64).reshape(-1, 3)
+        k += 1
+    out['count'] = np.array(k)
+    return out
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     pu, pe = ref_import.load_reference()
@@ -235,6 +258,7 @@ def main():
     np.savez_compressed(os.path.join(GOLD, 'ransac.npz'), **ransac_cases(pu, rng))
     np.savez_compressed(os.path.join(GOLD, 'ransac_inliers.npz'), **ransac_internal_cases(pu, rng))
     np.savez_compressed(os.path.join(GOLD, 'frames.npz'), **frame_cases(pu, pe))
+    np.savez_compressed(os.path.join(GOLD, 'clip.npz'), **clip_cases(pe, np.random.default_rng(77)))
     for f in sorted(os.listdir(GOLD)):
         print(f, os.path.getsize(os.path.join(GOLD, f)))
 

@@ -242,6 +242,27 @@ def camera_to_world(cam_pc, campose):
 
 
 # --------------------------------------------------------------------------- #
+# GT-box pre-filter  (clean_depth, pose_estimation.py:107-134, used at :293-299)
+# --------------------------------------------------------------------------- #
+def clip_to_box(depth_pts, gt_box, campose):
+    """Indices of the camera-space points whose world position lies strictly inside the
+    axis-aligned extent of the 8x3 GT box (pose_estimation.py:113-131)."""
+    lo, hi = gt_box.min(axis=0), gt_box.max(axis=0)                     # :113-118
+    world = camera_to_world(depth_pts.copy(), campose)                  # :120-122
+    keep = [i for i, q in enumerate(world)                              # :126-130
+            if q[0] > lo[0] and q[0] < hi[0] and q[1] > lo[1] and q[1] < hi[1] and q[2] > lo[2] and q[2] < hi[2]]
+    return np.asarray(keep, dtype=np.int64)
+
+
+def clipped_correspondence_indices(depth_pts, gt_box, campose, min_keep=20):
+    """run_pose's use of clean_depth (:293-299): the clip is only taken when more than 20 points survive."""
+    keep = clip_to_box(depth_pts, gt_box, campose)
+    if len(keep) > min_keep:                                            # :295
+        return keep
+    return np.arange(depth_pts.shape[0])
+
+
+# --------------------------------------------------------------------------- #
 # batched convenience used by tests / bench (loops the per-object oracle)
 # --------------------------------------------------------------------------- #
 def batch_pose(noc, depth, mask, bbox_xy0, intrinsics=None, sample_idx=None, ratio_adapt=1.0,

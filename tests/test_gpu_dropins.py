@@ -225,3 +225,38 @@ def test_batched_epilogue(pf):
     i = 0
     np.testing.assert_allclose(epi2.global_rot[i].cpu().numpy(), ora[i]['s'] * ora[i]['R'], rtol=1e-9, atol=1e-9)
     np.testing.assert_allclose(epi2.global_trans[i].cpu().numpy(), ora[i]['t'], rtol=1e-10)
+
+
+def test_gt_box_clip_mask(pf):
+    """posefit_clip_mask == clean_depth (pose_estimation.py:107-134) with run_pose's '> 20' rule (:293-299)."""
+    b, h, w = 10, 40, 48
+    d = pf.synth.make_objects(b, h, w, seed=93)
+    rng = np.random.default_rng(4)
+    campose = np.tile(np.identity(4), (b, 1, 1))
+    boxes = np.zeros((b, 8, 3))
+    corners = np.array([[sx, sy, sz] for sx in (-1, 1) for sy in (-1, 1) for sz in (-1, 1)], dtype=np.float64)
+    want_masks, want_kept = [], []
+    for i in range(b):
+        campose[i, :3, :3] = np.linalg.qr(rng.normal(size=(3, 3)))[0]
+        campose[i, :3, 3] = rng.normal(size=3)
+        x0, y0 = (int(v) for v in d['bbox_xy0'][i])
+        fd = np.zeros((240, 320), dtype=np.float32)
+        fm = np.zeros((240, 320), dtype=bool)
+        fd[y0:y0 + h, x0:x0 + w] = d['depth'][i].numpy()
+        fm[y0:y0 + h, x0:x0 + w] = d['mask'][i].numpy() != 0
+        pts, (rows, cols) = po.backproject_points(fd.astype(np.float64), po.motfront_intrinsics(), fm)
+        world = po.camera_to_world(pts, campose[i])
+        half = world.std(axis=0) * (0.02 if i == 3 else rng.uniform(0.5, 1.5))     # object 3: almost nothing survives
+        boxes[i] = (np.median(world, axis=0) + corners * half)[rng.permutation(8)]
+        keep = po.clipped_correspondence_indices(pts, boxes[i], campose[i])
+        m = np.zeros((h, w), dtype=np.uint8)
+        m[rows[keep] - y0, cols[keep] - x0] = 1
+        want_masks.append(m)
+        want_kept.append(len(keep))
+    got, kept = pf.clip_mask_to_box(d['depth'].cuda(), d['mask'].cuda(), d['bbox_xy0'].cuda(),
+                                    torch.from_numpy(boxes), torch.from_numpy(campose))
+    assert kept.cpu().tolist() == want_kept
+    assert want_kept[3] == int(d['n_valid'][3])                    # fallback to the unclipped set
+    assert any(k < int(n) for k, n in zip(want_kept, d['n_valid'].tolist()))
+    for i in range(b):
+        np.testing.assert_array_equal(got[i].cpu().numpy(), want_masks[i])

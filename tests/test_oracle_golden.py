@@ -131,3 +131,14 @@ def _paste(crop, xy0, dtype):
     h, w = crop.shape
     frame[int(xy0[1]):int(xy0[1]) + h, int(xy0[0]):int(xy0[0]) + w] = crop
     return frame
+
+
+def test_clip_to_box_matches_reference(golden_dir):
+    g = _load(golden_dir, 'clip.npz')
+    sizes = []
+    for k in range(int(g['count'])):
+        keep = po.clip_to_box(g[f'pts_{k}'], g[f'box_{k}'], g[f'campose_{k}'])
+        np.testing.assert_array_equal(keep, g[f'used_{k}'])
+        np.testing.assert_array_equal(g[f'pts_{k}'][keep].reshape(-1, 3), g[f'new_depth_{k}'])
+        sizes.append(len(keep))
+    assert min(sizes) <= 20 < max(sizes)          # both sides of run_pose's "> 20" rule are covered
