@@ -23,7 +23,8 @@ ABI_VERSION = 1
 SYMBOLS = ('posefit_version', 'posefit_error_string', 'posefit_workspace_bytes', 'posefit_forward',
            'posefit_forward_ransac', 'posefit_backward', 'posefit_backward_workspace_bytes', 'posefit_launch_count',
            'posefit_points_forward', 'posefit_points_forward_ransac', 'posefit_compact',
-           'posefit_points_evaluate', 'posefit_transform_points', 'posefit_epilogue', 'posefit_clip_mask')
+           'posefit_points_evaluate', 'posefit_transform_points', 'posefit_epilogue', 'posefit_clip_mask', 'posefit_sor_mask',
+           'posefit_sor_workspace_bytes')
 
 _lock = threading.Lock()
 _lib = None
@@ -83,6 +84,10 @@ def _declare(lib):
     lib.posefit_epilogue.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp, i32, vp, i32, i32, i32, vp, vp]
     lib.posefit_clip_mask.restype = i32
     lib.posefit_clip_mask.argtypes = [vp, vp, vp, vp, i32, vp, i32, vp, vp, i32, i32, i32, i32, vp, vp, vp]
+    lib.posefit_sor_workspace_bytes.restype = sz
+    lib.posefit_sor_workspace_bytes.argtypes = [i32, i32, i32]
+    lib.posefit_sor_mask.restype = i32
+    lib.posefit_sor_mask.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, f64, i32, i32, i32, i32, vp, vp, sz, vp]
     lib.posefit_transform_points.restype = i32
     lib.posefit_transform_points.argtypes = [vp, i32, vp, vp, i32, i32, vp]
 

@@ -257,6 +257,32 @@ def clip_mask_to_box(depth, mask, bbox_xy0, gt_box, campose, kinv=None, cam_inde
     return out, kept
 
 
+def statistical_outlier_mask(noc, depth, mask, bbox_xy0, kinv=None, source: str = 'depth', nb_neighbors: int = 20,
+                             std_ratio: float = 2.0, min_points: int = 100):
+    """Open3D-style statistical outlier removal as a mask filter (run_pose, pose_estimation.py:311-318
+    for source='depth', :341-349 for source='noc').  UNPINNED semantics (Open3D is not vendored).
+    Returns the surviving subset of mask & depth>0 as [B,H,W] u8."""
+    lib = _lib.lib()
+    if not depth.is_cuda:
+        raise _lib.PoseFitError('statistical_outlier_mask needs CUDA tensors: the solver has no CPU path')
+    dev = depth.device
+    b, h, w = (int(v) for v in depth.shape)
+    depth = depth.detach().to(torch.float32).contiguous()
+    mask = mask.to(device=dev, dtype=torch.uint8).contiguous()
+    bbox_xy0 = bbox_xy0.to(device=dev, dtype=torch.int32).contiguous()
+    if noc is not None:
+        noc = noc.detach().to(device=dev, dtype=torch.float32).contiguous()
+    kinv, per_obj = _prep_kinv(kinv, dev, b)
+    ws = torch.empty(max(int(lib.posefit_sor_workspace_bytes(b, h, w)), 8), dtype=torch.uint8, device=dev)
+    out = torch.empty_like(mask)
+    with torch.cuda.device(dev):
+        code = lib.posefit_sor_mask(_ptr(noc), _ptr(depth), _ptr(mask), _ptr(bbox_xy0), _ptr(kinv), per_obj,
+                                    {'depth': 0, 'noc': 1}[source], int(nb_neighbors), float(std_ratio),
+                                    int(min_points), b, h, w, _ptr(out), _ptr(ws), ws.numel(), _stream(dev))
+    _lib.check(code, 'posefit_sor_mask')
+    return out
+
+
 class PoseFit(torch.autograd.Function):
     """(scale[B], R[B,3,3], t[B,3], inlier_mask[B,H,W] u8, status[B] i32, n_valid[B] i32) =
     PoseFit.apply(noc, depth, mask, bbox_xy0, kinv, sample_idx, ratio_adapt, ref_compat).

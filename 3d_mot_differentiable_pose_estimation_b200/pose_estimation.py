@@ -2,9 +2,10 @@
 `transform_pc`, `cam2world`, `sort_bbox`, `run_pose`, `run_pose_office` with the reference's
 signatures and return types, computed by the CUDA library.
 
-Not reproduced (third-party, unpinned -- see DESIGN.md section 7): the Open3D
-`remove_statistical_outlier` passes (pose_estimation.py:311-318, :341-349).  The GT-box clip
-`clean_depth` (:107-134, :293-299) IS reproduced (posefit_clip_mask) when `gt_3d_box` is given.  The world box is the axis-aligned box of the depth
+The GT-box clip `clean_depth` (:107-134, :293-299) is reproduced (posefit_clip_mask) when
+`gt_3d_box` is given.  The two Open3D `remove_statistical_outlier` passes (:311-318, :341-349) are
+reproduced by posefit_sor_mask from Open3D's published algorithm; open3d==0.10.0.0 is not vendored,
+so that filter's parity is UNPINNED; set APPLY_STATISTICAL_FILTER = False to skip it.  The world box is the axis-aligned box of the depth
 points in Open3D's corner order followed by the reference's own `sort_bbox`.
 """
 from __future__ import annotations
@@ -13,12 +14,15 @@ import numpy as np
 import torch
 
 from . import _lib
-from .function import pose_fit_raw, default_kinv, clip_mask_to_box, _ptr, _stream
+from .function import pose_fit_raw, default_kinv, clip_mask_to_box, statistical_outlier_mask, _ptr, _stream
 
 __all__ = ['backproject', 'transform_pc', 'cam2world', 'sort_bbox', 'run_pose', 'run_pose_office']
 
 FOCAL = 292.87803547399                      # pose_estimation.py:272-273
 N_ITERATIONS, N_SAMPLES = 100, 10            # pose_utils.py:97, :73
+# run_pose applies Open3D's statistical outlier removal twice (:311-318, :341-349); our restatement
+# of it is unpinned, so it can be switched off to fit on all mask & depth>0 correspondences
+APPLY_STATISTICAL_FILTER = True
 
 
 def _device():
@@ -128,6 +132,9 @@ def _run(nocs, depth, kinv, campose, bin_mask, abs_bbox, use_depth_box, gt_3d_bo
     if gt_3d_box is not None and campose is not None:                   # clean_depth, :293-299
         m, _ = clip_mask_to_box(d, m, xy0, torch.as_tensor(_np(gt_3d_box)).reshape(1, 8, 3),
                                 torch.as_tensor(_np(campose)), kinv)
+    if APPLY_STATISTICAL_FILTER:
+        m = statistical_outlier_mask(None, d, m, xy0, kinv, source='depth')     # :311-318
+        m = statistical_outlier_mask(noc, d, m, xy0, kinv, source='noc')        # :341-349
     src, dst, rows, cols = _compact(noc[0], d[0], m[0], xy0, kinv)
     n = int(dst.shape[0])
     if n == 0:                                                          # :361-362

@@ -37,8 +37,8 @@ UNIT = 'objects/s'
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=10)
-    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--steps', type=int, default=100)
+    ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--objects', type=int, default=SEQ_PER_GPU * FRAMES_PER_SEQ * OBJ_PER_FRAME,
                     help='objects per GPU per step (default: config-5 shard, 125000)')
@@ -126,7 +126,7 @@ def cpu_baseline(pf, size, n_sample, kind='port'):
     n1 = max(8, n_sample // max(cores, 1))
     one, _ = cpu_objects_per_s(_subsample(sample, n1), with_bwd=True, procs=1)
     fwd, _ = cpu_objects_per_s(sample, with_bwd=False)
-    n_r = max(cores, min(n_sample, 8 * cores))
+    n_r = max(cores, min(n_sample, 48 * cores))
     rans, _ = cpu_objects_per_s(_subsample(sample, n_r), with_bwd=False, ransac=True)
     return {'value': value, 'unit': UNIT, 'cores': cores, 'kind': kind, 'cpu_model': cpu_model(),
             'single_core_value': one,
@@ -155,7 +155,7 @@ class ClockSampler:
                 self.samples.append([x.strip() for x in out.strip().split(',')])
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.05)
 
     def __enter__(self):
         self.th = threading.Thread(target=self._run, daemon=True)
@@ -331,7 +331,7 @@ def run_ours(args):
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    k_e2e = max(3, min(args.steps, 10))
+    k_e2e = max(3, min(args.steps, 20))
     t0, t1 = ev(), ev()
     t0.record()
     for _ in range(k_e2e):
@@ -406,7 +406,7 @@ def run_ours(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        n_cpu = args.cpu_sample or 64 * (os.cpu_count() or 1)
+        n_cpu = args.cpu_sample or 256 * (os.cpu_count() or 1)
         cpu = cpu_baseline(pf, size, n_cpu)
 
     if rank == 0:

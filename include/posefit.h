@@ -183,6 +183,20 @@ int posefit_clip_mask(const float* depth, const uint8_t* mask, const int32_t* bb
                       const double* gt_box, int min_keep, int n_objects, int height, int width,
                       uint8_t* out_mask, int32_t* kept, void* stream);
 
+/* Statistical outlier removal as a mask filter: the Open3D remove_statistical_outlier(20, 2.0)
+ * passes of run_pose (PoseEst/pose_estimation.py:311-318 on the depth cloud = source 0, :341-349 on
+ * the NOC cloud = source 1; applied only when the cloud has more than min_points = 100 points).
+ * UNPINNED: open3d==0.10.0.0 is not vendored; the semantics are restated from Open3D's
+ * PointCloud::RemoveStatisticalOutliers (mean distance to the nb_neighbors nearest points, the query
+ * itself included; threshold = mean + std_ratio * sample std).  nb_neighbors must be 20.
+ * out_mask[b] = the surviving subset of (mask & depth > 0); chain two calls (depth, then NOC on the
+ * first call's out_mask) to reproduce run_pose. */
+size_t posefit_sor_workspace_bytes(int n_objects, int height, int width);
+int posefit_sor_mask(const float* noc, const float* depth, const uint8_t* mask, const int32_t* bbox_xy0,
+                     const double* kinv, int kinv_per_object, int source, int nb_neighbors, double std_ratio,
+                     int min_points, int n_objects, int height, int width, uint8_t* out_mask,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
 /* Number of kernels this library has launched in the calling process (for bench.py's
  * gpu_launches claim). */
 unsigned long long posefit_launch_count(void);

@@ -263,6 +263,39 @@ def clipped_correspondence_indices(depth_pts, gt_box, campose, min_keep=20):
 
 
 # --------------------------------------------------------------------------- #
+# statistical outlier removal -- UNPINNED (Open3D 0.10 is not vendored / installed)
+# --------------------------------------------------------------------------- #
+def statistical_outlier_indices(points, nb_neighbors=20, std_ratio=2.0):
+    """Restatement of open3d.geometry.PointCloud.remove_statistical_outlier as run_pose calls it
+    (pose_estimation.py:312, :342): mean distance of every point to its nb_neighbors nearest
+    points (itself included), threshold = mean + std_ratio * sample std, keep 0 < avg < threshold.
+    Returns the kept indices in ascending order.  Parity unpinned: written from Open3D's published
+    algorithm, not checked against the library."""
+    from scipy.spatial import cKDTree
+    n = points.shape[0]
+    if n == 0:
+        return np.zeros(0, dtype=np.int64)
+    dist, _ = cKDTree(points).query(points, k=min(nb_neighbors, n))
+    dist = dist.reshape(n, -1)
+    avg = dist.mean(axis=1)
+    valid = avg > 0
+    mean = avg[valid].sum() / n
+    std = np.sqrt(((avg[valid] - mean) ** 2).sum() / (n - 1))
+    return np.where(valid & (avg < mean + std_ratio * std))[0]
+
+
+def run_pose_filters(noc_pts, depth_pts, min_points=100):
+    """The two filter passes of run_pose (pose_estimation.py:311-318, :341-349): returns the indices
+    (into the input correspondences) that survive both."""
+    keep = np.arange(depth_pts.shape[0])
+    if depth_pts.shape[0] > min_points:                                 # :311
+        keep = statistical_outlier_indices(depth_pts)
+    if len(keep) > min_points:                                          # :341
+        keep = keep[statistical_outlier_indices(noc_pts[keep])]
+    return keep
+
+
+# --------------------------------------------------------------------------- #
 # batched convenience used by tests / bench (loops the per-object oracle)
 # --------------------------------------------------------------------------- #
 def batch_pose(noc, depth, mask, bbox_xy0, intrinsics=None, sample_idx=None, ratio_adapt=1.0,

@@ -142,6 +142,9 @@ def test_run_pose_against_oracle(pf, monkeypatch):
         campose[:3, 3] = rng.normal(size=3)
         bbox = (x0, y0, x0 + w, y0 + h)
         noc_pts, depth_pts, _ = po.crop_correspondences(noc_hwc.numpy(), depth, mask, bbox)
+        keep = po.run_pose_filters(noc_pts, depth_pts)                  # the two statistical filters
+        assert 100 < len(keep) < noc_pts.shape[0]
+        noc_pts, depth_pts = noc_pts[keep], depth_pts[keep]
         idx = rng.integers(0, noc_pts.shape[0], size=(100, 10))
         ora = po.pose_from_correspondences(noc_pts, depth_pts, idx)
         with replay(idx):
@@ -260,3 +263,33 @@ def test_gt_box_clip_mask(pf):
     assert any(k < int(n) for k, n in zip(want_kept, d['n_valid'].tolist()))
     for i in range(b):
         np.testing.assert_array_equal(got[i].cpu().numpy(), want_masks[i])
+
+
+def test_statistical_outlier_mask(pf):
+    """posefit_sor_mask vs the oracle restatement of Open3D's remove_statistical_outlier (unpinned)."""
+    b, h, w = 6, 48, 56
+    d = pf.synth.make_objects(b, h, w, seed=95)
+    d['mask'][4] = 0
+    d['mask'][4, 10:14, 10:20] = 1                        # 40 points: below the 100-point rule -> untouched
+    t = {k: d[k].cuda() for k in ('noc', 'depth', 'mask', 'bbox_xy0')}
+    m1 = pf.statistical_outlier_mask(None, t['depth'], t['mask'], t['bbox_xy0'], source='depth')
+    m2 = pf.statistical_outlier_mask(t['noc'], t['depth'], m1, t['bbox_xy0'], source='noc')
+    for i in range(b):
+        x0, y0 = (int(v) for v in d['bbox_xy0'][i])
+        fd = np.zeros((240, 320), dtype=np.float32)
+        fm = np.zeros((240, 320), dtype=bool)
+        fd[y0:y0 + h, x0:x0 + w] = d['depth'][i].numpy()
+        fm[y0:y0 + h, x0:x0 + w] = d['mask'][i].numpy() != 0
+        noc_pts, depth_pts, (rows, cols) = po.crop_correspondences(np.transpose(d['noc'][i].numpy(), (1, 2, 0)), fd, fm,
+                                                                   (x0, y0, x0 + w, y0 + h))
+        k1 = po.statistical_outlier_indices(depth_pts) if depth_pts.shape[0] > 100 else np.arange(depth_pts.shape[0])
+        want1 = np.zeros((h, w), dtype=np.uint8)
+        want1[rows[k1] - y0, cols[k1] - x0] = 1
+        np.testing.assert_array_equal(m1[i].cpu().numpy(), want1)
+        k2 = po.run_pose_filters(noc_pts, depth_pts)
+        want2 = np.zeros((h, w), dtype=np.uint8)
+        want2[rows[k2] - y0, cols[k2] - x0] = 1
+        np.testing.assert_array_equal(m2[i].cpu().numpy(), want2)
+    n4 = int(((d['mask'][4] != 0) & (d['depth'][4] > 0)).sum())
+    assert 30 <= n4 <= 40 and int(m1[4].sum()) == n4     # fewer than 100 points: left untouched (:311)
+    assert int(m1[0].sum()) < int(d['n_valid'][0])        # the gross outliers are gone
