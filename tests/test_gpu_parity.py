@@ -316,3 +316,79 @@ def test_full_size_properties(pf):
     assert float((R2 - R[:, :, perm]).abs().max()) < 1e-9
     assert float((raw2.pose[:, 0] - raw.pose[:, 0]).abs().max() / raw.pose[:, 0].abs().max()) < 1e-12
     assert float((raw2.pose[:, 10:13] - raw.pose[:, 10:13]).abs().max()) < 1e-9
+
+
+def test_cuda_graph_capture_and_streams(pf):
+    """include/posefit.h promises: asynchronous on the caller's stream, no host reads, graph capturable."""
+    d = pf.synth.make_objects(96, 64, 64, seed=71, device='cuda', n_hyp=32)
+    kinv = pf.default_kinv('cuda')
+    g = (torch.randn(96, device='cuda'), torch.randn(96, 9, device='cuda'), torch.randn(96, 3, device='cuda'))
+
+    def work():
+        raw = pf.pose_fit_raw(d['noc'], d['depth'], d['mask'], d['bbox_xy0'], kinv)
+        rr = pf.pose_fit_raw(d['noc'], d['depth'], d['mask'], d['bbox_xy0'], kinv, sample_idx=d['sample_idx'])
+        gn, _ = pf.pose_fit_backward_raw(d['noc'], d['depth'], d['mask'], None, d['bbox_xy0'], kinv, raw.ctx, raw.status, *g)
+        return raw.pose, rr.pose, rr.inlier_mask, gn
+
+    eager = [t.clone() for t in work()]
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        work()
+        side.synchronize()
+        with torch.cuda.graph(graph, stream=side):
+            captured = work()
+    torch.cuda.current_stream().wait_stream(side)
+    for t in captured:
+        t.zero_()
+    graph.replay()
+    torch.cuda.synchronize()
+    for a, b in zip(eager, captured):
+        assert torch.equal(a, b)
+    # two streams, two different batches, interleaved launches
+    d2 = pf.synth.make_objects(96, 64, 64, seed=72, device='cuda')
+    ref1 = pf.pose_fit_raw(d['noc'], d['depth'], d['mask'], d['bbox_xy0'], kinv).pose.clone()
+    ref2 = pf.pose_fit_raw(d2['noc'], d2['depth'], d2['mask'], d2['bbox_xy0'], kinv).pose.clone()
+    torch.cuda.synchronize()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    outs = []
+    for _ in range(4):
+        with torch.cuda.stream(s1):
+            o1 = pf.pose_fit_raw(d['noc'], d['depth'], d['mask'], d['bbox_xy0'], kinv).pose
+        with torch.cuda.stream(s2):
+            o2 = pf.pose_fit_raw(d2['noc'], d2['depth'], d2['mask'], d2['bbox_xy0'], kinv).pose
+        outs.append((o1, o2))
+    torch.cuda.synchronize()
+    for o1, o2 in outs:
+        assert torch.equal(o1, ref1) and torch.equal(o2, ref2)
+
+
+def test_full_size_ransac_properties(pf):
+    """BASELINE config 3 size (4096 x 64x64, 128 hypotheses): oracle on a 48-object sample, and
+    size-independent properties on everything: inliers are a subset of the valid pixels, the
+    refit uses exactly the inliers, R orthonormal, determinism (bitwise equal on a second run)."""
+    b = 4096
+    d = pf.synth.make_objects(b, 64, 64, seed=81, device='cuda', n_hyp=128)
+    a = pf.pose_fit_raw(d['noc'], d['depth'], d['mask'], d['bbox_xy0'], sample_idx=d['sample_idx'])
+    c = pf.pose_fit_raw(d['noc'], d['depth'], d['mask'], d['bbox_xy0'], sample_idx=d['sample_idx'])
+    assert torch.equal(a.pose, c.pose) and torch.equal(a.inlier_mask, c.inlier_mask) and torch.equal(a.winner, c.winner)
+    valid = (d['mask'] != 0) & (d['depth'] > 0)
+    assert int((a.inlier_mask.bool() & ~valid).sum()) == 0
+    ok = a.status == 0
+    assert int(ok.sum()) >= b - 8
+    n_inl = a.inlier_mask.flatten(1).sum(1).to(torch.float64)
+    assert torch.equal(n_inl[ok], a.pose[ok, 13])
+    R = a.pose[:, 1:10].reshape(b, 3, 3)
+    eye = torch.eye(3, dtype=torch.float64, device='cuda')
+    assert float((R @ R.transpose(1, 2) - eye).abs().max()) < 1e-12
+    assert int(((a.winner < 0) | (a.winner >= 128))[ok].sum()) == 0
+    # refit == plain fit restricted to the inlier mask
+    plain = pf.pose_fit_raw(d['noc'], d['depth'], a.inlier_mask, d['bbox_xy0'])
+    assert float((plain.pose[ok, :13] - a.pose[ok, :13]).abs().max()) < 1e-9
+    sel = slice(1000, 1048)
+    ora = po.batch_pose(d['noc'][sel].cpu().numpy(), d['depth'][sel].cpu().numpy(), d['mask'][sel].cpu().numpy(),
+                        d['bbox_xy0'][sel].cpu().numpy(), sample_idx=d['sample_idx'][sel].cpu().numpy())
+    sub = pf.PoseFitRaw(a.pose[sel], a.ctx[sel], a.status[sel], a.n_valid[sel], a.inlier_mask[sel], a.winner[sel])
+    check_against_oracle(sub, ora, ransac=True)
