@@ -24,7 +24,8 @@ SYMBOLS = ('posefit_version', 'posefit_error_string', 'posefit_workspace_bytes',
            'posefit_forward_ransac', 'posefit_backward', 'posefit_backward_workspace_bytes', 'posefit_launch_count',
            'posefit_points_forward', 'posefit_points_forward_ransac', 'posefit_compact',
            'posefit_points_evaluate', 'posefit_transform_points', 'posefit_epilogue', 'posefit_clip_mask', 'posefit_sor_mask',
-           'posefit_sor_workspace_bytes')
+           'posefit_sor_workspace_bytes', 'posefit_resample_noc', 'posefit_resample_noc_backward',
+           'posefit_gather_crops')
 
 _lock = threading.Lock()
 _lib = None
@@ -88,6 +89,12 @@ def _declare(lib):
     lib.posefit_sor_workspace_bytes.argtypes = [i32, i32, i32]
     lib.posefit_sor_mask.restype = i32
     lib.posefit_sor_mask.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, f64, i32, i32, i32, i32, vp, vp, sz, vp]
+    lib.posefit_resample_noc.restype = i32
+    lib.posefit_resample_noc.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp, vp]
+    lib.posefit_resample_noc_backward.restype = i32
+    lib.posefit_resample_noc_backward.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp, vp]
+    lib.posefit_gather_crops.restype = i32
+    lib.posefit_gather_crops.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp]
     lib.posefit_transform_points.restype = i32
     lib.posefit_transform_points.argtypes = [vp, i32, vp, vp, i32, i32, vp]
 

@@ -197,6 +197,26 @@ int posefit_sor_mask(const float* noc, const float* depth, const uint8_t* mask, 
                      int min_points, int n_objects, int height, int width, uint8_t* out_mask,
                      void* workspace, size_t workspace_bytes, void* stream);
 
+/* Batched front end of the per-instance loop (Detection/tracker/postprocess.py:131-152).
+ *
+ * posefit_resample_noc: the ROI-align resize of the NOC head output head[b][3][head_h][head_w]
+ * (3 x 28 x 28, Detection/roi_heads/nocs_head.py:232-235) to each instance's box size
+ * roi_hw[b] = (h_b, w_b) (postprocess.py:141-147: roi_align over the whole map, aligned=True,
+ * sampling_ratio -1), written zero-padded into noc[b][3][H][W].  Same arithmetic as
+ * torchvision.ops.roi_align, which detectron2.layers.roi_align wraps.
+ * posefit_resample_noc_backward: its adjoint, grad_head[b][3][head_h][head_w] (fully written).
+ * posefit_gather_crops: depth[b][H][W] / mask[b][H][W] = the bbox window of frame frame_of[b] of
+ * depth_frames[F][FH][FW] and of the instance's full-frame mask mask_frames[b][FH][FW]
+ * (PoseEst/pose_estimation.py:260-262, :290), zero outside the box; bbox_xyxy[b] = integer
+ * (x0, y0, x1, y1), upper corner exclusive; also writes bbox_xy0[b] and roi_hw[b]. */
+int posefit_resample_noc(const float* head, const int32_t* roi_hw, int n_objects, int head_h, int head_w,
+                         int height, int width, float* noc, void* stream);
+int posefit_resample_noc_backward(const float* grad_noc, const int32_t* roi_hw, int n_objects, int head_h,
+                                  int head_w, int height, int width, float* grad_head, void* stream);
+int posefit_gather_crops(const float* depth_frames, const uint8_t* mask_frames, const int32_t* frame_of,
+                         const int32_t* bbox_xyxy, int n_objects, int frame_h, int frame_w, int height, int width,
+                         float* depth, uint8_t* mask, int32_t* bbox_xy0, int32_t* roi_hw, void* stream);
+
 /* Number of kernels this library has launched in the calling process (for bench.py's
  * gpu_launches claim). */
 unsigned long long posefit_launch_count(void);

@@ -1,0 +1,105 @@
+"""Batched front end (gather_crops, resample_noc) against torchvision.ops.roi_align -- the function
+detectron2.layers.roi_align wraps and the reference calls per instance (postprocess.py:141-147) --
+and NumPy slicing (pose_estimation.py:260-262, :290)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_pkg
+from oracle import posefit_oracle as po
+
+pytestmark = pytest.mark.gpu
+tv_ops = pytest.importorskip('torchvision.ops')
+
+
+@pytest.fixture(scope='module')
+def pf():
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    return load_pkg()
+
+
+def _reference_patch(head_i, h, w):
+    """postprocess.py:141-147 for one instance (CPU)."""
+    box = [torch.tensor([[0.0, 0.0, float(head_i.shape[1]), float(head_i.shape[2])]])]
+    return tv_ops.roi_align(head_i[None], box, output_size=(h, w), aligned=True)[0]
+
+
+def test_resample_noc_matches_roi_align(pf):
+    gen = torch.Generator().manual_seed(3)
+    sizes = [(64, 64), (20, 33), (112, 90), (3, 5), (28, 28), (57, 14), (1, 1), (100, 7)]
+    b, H, W = len(sizes), 112, 96
+    head = torch.rand(b, 3, 28, 28, generator=gen)
+    roi_hw = torch.tensor(sizes, dtype=torch.int32)
+    got = pf.resample_noc(head.cuda(), roi_hw.cuda(), H, W).cpu()
+    for i, (h, w) in enumerate(sizes):
+        want = _reference_patch(head[i], h, w)
+        np.testing.assert_allclose(got[i, :, :h, :w].numpy(), want.numpy(), rtol=0, atol=2e-7)
+        assert float(got[i, :, h:, :].abs().max() if h < H else 0.0) == 0.0
+        assert float(got[i, :, :, w:].abs().max() if w < W else 0.0) == 0.0
+
+
+def test_resample_noc_backward_matches_autograd(pf):
+    gen = torch.Generator().manual_seed(4)
+    sizes = [(64, 64), (20, 33), (9, 40), (80, 96)]
+    b, H, W = len(sizes), 80, 96
+    head = torch.rand(b, 3, 28, 28, generator=gen)
+    g = torch.randn(b, 3, H, W, generator=gen)
+    hc = head.cuda().requires_grad_(True)
+    out = pf.resample_noc(hc, torch.tensor(sizes, dtype=torch.int32).cuda(), H, W)
+    out.backward(g.cuda())
+    for i, (h, w) in enumerate(sizes):
+        hi = head[i].clone().requires_grad_(True)
+        _reference_patch(hi, h, w).backward(g[i, :, :h, :w])
+        np.testing.assert_allclose(hc.grad[i].cpu().numpy(), hi.grad.numpy(), rtol=1e-4, atol=1e-5)
+
+
+def test_gather_crops_matches_slicing(pf):
+    rng = np.random.default_rng(5)
+    F, FH, FW, H, W = 3, 240, 320, 72, 80
+    depth = rng.uniform(0.5, 6.0, size=(F, FH, FW)).astype(np.float32)
+    boxes = np.array([[10, 20, 74, 84], [100, 50, 180, 120], [300, 200, 320, 240], [0, 0, 5, 3], [50, 60, 50, 90],
+                      [200, 100, 290, 190]], dtype=np.int32)          # the last one is larger than HxW
+    b = boxes.shape[0]
+    frame_of = np.array([0, 1, 2, 0, 1, 2], dtype=np.int32)
+    masks = rng.uniform(size=(b, FH, FW)) < 0.6
+    c = pf.gather_crops(torch.from_numpy(depth).cuda(), torch.from_numpy(masks).cuda(), torch.from_numpy(boxes).cuda(),
+                        torch.from_numpy(frame_of).cuda(), H, W)
+    for i in range(b):
+        x0, y0, x1, y1 = boxes[i]
+        h, w = min(y1 - y0, H), min(x1 - x0, W)
+        assert c.roi_hw[i].cpu().tolist() == [h, w] and c.bbox_xy0[i].cpu().tolist() == [x0, y0]
+        want_d = np.zeros((H, W), dtype=np.float32)
+        want_m = np.zeros((H, W), dtype=np.uint8)
+        want_d[:h, :w] = depth[frame_of[i], y0:y0 + h, x0:x0 + w]
+        want_m[:h, :w] = masks[i, y0:y0 + h, x0:x0 + w]
+        np.testing.assert_array_equal(c.depth[i].cpu().numpy(), want_d)
+        np.testing.assert_array_equal(c.mask[i].cpu().numpy(), want_m)
+
+
+def test_batched_pipeline_equals_per_instance_reference_flow(pf):
+    """head output + frame depth + instance masks + boxes -> poses, in three launches, equals the
+    per-instance flow of postprocess.py:131-152 + run_pose (oracle, no filters, plain fit)."""
+    rng = np.random.default_rng(6)
+    gen = torch.Generator().manual_seed(6)
+    b, FH, FW, H, W = 5, 240, 320, 64, 72
+    boxes = np.array([[40, 30, 100, 94], [150, 60, 222, 110], [10, 150, 60, 214], [200, 120, 264, 180], [90, 90, 131, 123]],
+                     dtype=np.int32)
+    head = torch.rand(b, 3, 28, 28, generator=gen)
+    depth = rng.uniform(2.0, 5.0, size=(1, FH, FW)).astype(np.float32)
+    masks = rng.uniform(size=(b, FH, FW)) < 0.7
+    crops = pf.gather_crops(torch.from_numpy(depth).cuda(), torch.from_numpy(masks).cuda(), torch.from_numpy(boxes).cuda(),
+                            None, H, W)
+    noc = pf.resample_noc(head.cuda(), crops.roi_hw, H, W)
+    raw = pf.pose_fit_raw(noc, crops.depth, crops.mask, crops.bbox_xy0)
+    for i in range(b):
+        x0, y0, x1, y1 = boxes[i]
+        patch = _reference_patch(head[i], y1 - y0, x1 - x0).permute(1, 2, 0).contiguous().numpy()   # HxWxC, :147
+        noc_pts, depth_pts, _ = po.crop_correspondences(patch, depth[0], masks[i], boxes[i])
+        o = po.pose_from_correspondences(noc_pts, depth_pts)
+        pose = raw.pose[i].cpu().numpy()
+        assert int(raw.status[i]) == o['status'] == 0 and int(raw.n_valid[i]) == o['n_valid']
+        ang = np.degrees(np.linalg.norm(pose[1:10].reshape(3, 3) - o['R']) / np.sqrt(2))
+        assert ang <= 1e-3
+        np.testing.assert_allclose(pose[0], o['s'], rtol=1e-5)
+        np.testing.assert_allclose(pose[10:13], o['t'], rtol=1e-5)

@@ -23,7 +23,8 @@ def test_library_exports_every_declared_symbol():
     assert {'posefit_forward', 'posefit_forward_ransac', 'posefit_backward', 'posefit_points_forward',
             'posefit_points_forward_ransac', 'posefit_compact', 'posefit_points_evaluate',
             'posefit_transform_points', 'posefit_epilogue', 'posefit_clip_mask', 'posefit_sor_mask',
-            'posefit_sor_workspace_bytes', 'posefit_workspace_bytes', 'posefit_backward_workspace_bytes', 'posefit_version',
+            'posefit_sor_workspace_bytes', 'posefit_resample_noc', 'posefit_resample_noc_backward',
+            'posefit_gather_crops', 'posefit_workspace_bytes', 'posefit_backward_workspace_bytes', 'posefit_version',
             'posefit_error_string', 'posefit_launch_count'} <= declared
     handle = ctypes.CDLL(path)
     for name in declared:
