@@ -15,6 +15,7 @@ from .function import (PoseFit, PoseFitRaw, pose_fit, pose_fit_raw, points_fit_r
                        STATUS_OK, STATUS_EMPTY, STATUS_LOW_INLIER_RATIO, STATUS_NAN)
 from . import synth, shard  # noqa: F401
 from .frontend import gather_crops, resample_noc, ResampleNoc, Crops  # noqa: F401
+from . import graph_dataset  # noqa: F401  (drop-in for Tracking/datasets/graph_dataset.py's edge construction)
 from . import pose_utils, pose_estimation  # noqa: F401  (drop-ins for PoseEst/pose_utils.py, pose_estimation.py)
 
 __all__ = ['PoseFit', 'PoseFitRaw', 'pose_fit', 'pose_fit_raw', 'points_fit_raw', 'pose_fit_backward_raw',

@@ -25,7 +25,7 @@ SYMBOLS = ('posefit_version', 'posefit_error_string', 'posefit_workspace_bytes',
            'posefit_points_forward', 'posefit_points_forward_ransac', 'posefit_compact',
            'posefit_points_evaluate', 'posefit_transform_points', 'posefit_epilogue', 'posefit_clip_mask', 'posefit_sor_mask',
            'posefit_sor_workspace_bytes', 'posefit_resample_noc', 'posefit_resample_noc_backward',
-           'posefit_gather_crops')
+           'posefit_gather_crops', 'posefit_edge_features', 'posefit_edge_workspace_bytes')
 
 _lock = threading.Lock()
 _lib = None
@@ -95,6 +95,11 @@ def _declare(lib):
     lib.posefit_resample_noc_backward.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp, vp]
     lib.posefit_gather_crops.restype = i32
     lib.posefit_gather_crops.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp]
+    lib.posefit_edge_workspace_bytes.restype = sz
+    lib.posefit_edge_workspace_bytes.argtypes = [i32, i32, i32, i32]
+    lib.posefit_edge_features.restype = i32
+    lib.posefit_edge_features.argtypes = [vp, vp, vp, i32, vp, vp, i32, i32, i32, i32, i32, c.c_longlong,
+                                          vp, vp, vp, vp, vp, vp, vp, sz, vp]
     lib.posefit_transform_points.restype = i32
     lib.posefit_transform_points.argtypes = [vp, i32, vp, vp, i32, i32, vp]
 

@@ -20,8 +20,10 @@
 
 #if defined(__CUDACC__)
 #define PF_HD __host__ __device__ __forceinline__
+#define PF_NOINLINE __host__ __device__ __noinline__
 #else
 #define PF_HD inline
+#define PF_NOINLINE inline
 #endif
 
 namespace posefit {
@@ -263,6 +265,17 @@ struct Fit {
 
 enum { PF_OK = 0, PF_EMPTY = 1, PF_LOW_INLIER_RATIO = 2, PF_NAN = 3 };
 
+// Cold path of solve_rotation, kept out of line so the straight-line code a solve walks through
+// (and has to fetch: these kernels run once per object, instruction-cache cold) stays short.
+struct Mat3 { double m[9]; };
+PF_NOINLINE Mat3 rotation_redo(Mat3 C, Mat3 Cn) {
+  Mat3 R;
+  rotation_start<double, 6>(C.m, R.m);
+  newton_step(Cn.m, R.m);
+  newton_step(Cn.m, R.m);
+  return R;
+}
+
 // Rotation maximising tr(R^T C) over SO(3) plus H (and Linv when WANT_LINV).
 // Start: one-sided Jacobi in float (3 sweeps, ~1e-6), one Newton-Schulz orthonormalisation, then
 // Newton steps on SO(3) in double.  Newton converges quadratically, so the skew residual measured
@@ -283,14 +296,30 @@ PF_HD void solve_rotation(const double* C, double* R, double* H, double* Linv) {
 #pragma unroll
   for (int i = 0; i < 9; ++i) Cn[i] = C[i] * inv;
   orthonormalize_step(R);
-  newton_step(Cn, R);
-  const double kn = newton_step(Cn, R);       // residual BEFORE the second step
-  if (!(kn < 1e-8)) {                         // not in the quadratic regime: redo from a double start
-    rotation_start<double, 6>(C, R);
-    newton_step(Cn, R);
-    newton_step(Cn, R);
+  // Newton steps share ONE loop body (code size); kn = residual BEFORE the second step.  If it has
+  // not collapsed the start was outside the quadratic regime: redo from a double-precision start.
+  double kn = 0.0;
+#pragma unroll 1
+  for (int it = 0; it < (EXTRA_STEP ? 3 : 2); ++it) {
+    if (it == 2 && !(kn < 1e-8)) {
+      Mat3 c3, cn3;
+#pragma unroll
+      for (int i = 0; i < 9; ++i) { c3.m[i] = C[i]; cn3.m[i] = Cn[i]; }
+      const Mat3 r3 = rotation_redo(c3, cn3);
+#pragma unroll
+      for (int i = 0; i < 9; ++i) R[i] = r3.m[i];
+    }
+    const double k = newton_step(Cn, R);
+    if (it == 1) kn = k;
   }
-  if (EXTRA_STEP) newton_step(Cn, R);
+  if (!EXTRA_STEP && !(kn < 1e-8)) {
+    Mat3 c3, cn3;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) { c3.m[i] = C[i]; cn3.m[i] = Cn[i]; }
+    const Mat3 r3 = rotation_redo(c3, cn3);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) R[i] = r3.m[i];
+  }
   orthonormalize_step(R);
   double M[9];
   rt_times(R, Cn, M);

@@ -217,6 +217,32 @@ int posefit_gather_crops(const float* depth_frames, const uint8_t* mask_frames, 
                          const int32_t* bbox_xyxy, int n_objects, int frame_h, int frame_w, int height, int width,
                          float* depth, uint8_t* mask, int32_t* bbox_xy0, int32_t* roi_hw, void* stream);
 
+/* Tracker graph edges from pose tensors: GraphDataset.get_edge_data and
+ * get_edge_data_office (Tracking/datasets/graph_dataset.py:30-199, :232-330), batched over
+ * n_sequences sequences of n_frames frames each.  Nodes are the detections in (sequence, frame)
+ * order; frame_start[s * n_frames + f] is the index of the first node of frame f of sequence s
+ * (n_sequences * n_frames + 1 entries).  translations / rotations (XYZ Euler) [N][3] and
+ * scales [N][scale_dim] are float64, the per-frame hdf5 records of
+ * Detection/inference_detector.py:352-371 concatenated as Tracking/mpn_trainer.py:440-442 does.
+ * node_id[n] = what train_utils.check_pair returned for the node (ground-truth object id, < 0 for
+ * None); NULL keeps every pair (the _office variant).  Candidate pairs (n in frame t, m in frame
+ * t+1 .. t+max_frame_dist, frame < min(max_seq_len, n_frames)) are emitted in the reference's loop
+ * order:  edge_index[0][e], edge_index[1][e] (row stride max_edges, node indices local to the
+ * sequence), edge_attr[e] = { t_m - t_n (3), euler_m - euler_n (3), log(scale_m / scale_n)
+ * (scale_dim), frame distance } as float32 (float64 arithmetic, rounded once, :166-199),
+ * targets[e] = (id_n == id_m), consecutive[e] = (frame == t + 1), edge_seq[e] = sequence.
+ * totals[0] = number of (directed) edges, totals[1] = the reference's false_positives count
+ * (:95-96, :133-136).  Edges beyond max_edges are dropped (totals still counts them).
+ * targets / consecutive / edge_seq may be NULL.  The undirected duplication of :203-206 is a plain
+ * concatenation and is left to the caller. */
+size_t posefit_edge_workspace_bytes(int n_sequences, int n_frames, int n_nodes, int max_frame_dist);
+int posefit_edge_features(const double* translations, const double* rotations, const double* scales, int scale_dim,
+                          const int32_t* frame_start, const int32_t* node_id, int n_sequences, int n_frames,
+                          int n_nodes, int max_frame_dist, int max_seq_len, long long max_edges,
+                          long long* edge_index, float* edge_attr, float* targets, int8_t* consecutive,
+                          int32_t* edge_seq, long long* totals, void* workspace, size_t workspace_bytes,
+                          void* stream);
+
 /* Number of kernels this library has launched in the calling process (for bench.py's
  * gpu_launches claim). */
 unsigned long long posefit_launch_count(void);
