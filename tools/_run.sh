@@ -1,6 +1,7 @@
-export PROBE_MODES=rotate POSEFIT_DEPTH=4
-for ed in 0 1 3 7 15 11 9; do echo "EARLY_DEP=$ed"; POSEFIT_EARLY_DEP=$ed python tools/latency_probe.py | grep rotate; done
-unset POSEFIT_DEPTH
-for ed in 1 15 9; do POSEFIT_EARLY_DEP=$ed python bench.py --steps 30 --warmup 3 --no-cpu --no-extra 2>/dev/null | python -c "
+python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+python bench.py --steps 10 --warmup 3 --no-cpu > gpurun_out/s8_bench.json 2>gpurun_out/s8_bench.err; python - <<'PY'
 import json,sys
-d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('ED=$ed', 'ms/step %.3f'%d['ms_per_step'], 'e2e %.3e'%d['e2e']['value'])"; done
+d=json.loads(open("gpurun_out/s8_bench.json").read().strip().splitlines()[-1])
+print("value %.3e ms/step %.3f e2e %.3e" % (d["value"], d["ms_per_step"], d["e2e"]["value"]))
+for k,v in d["configs"].items(): print("  %-32s %.4f ms frac %.3f" % (k, v["ms"], v["frac"]))
+PY
