@@ -45,6 +45,16 @@ PF_HD double pf_rsqrt(double x) {
   return 1.0 / sqrt(x);
 #endif
 }
+// a / b for the Jacobi rotation angles: the float start only has to land inside Newton's quadratic
+// basin, so the device takes the 2-ulp MUFU-based quotient instead of the IEEE sequence
+PF_HD float pf_div(float a, float b) {
+#if defined(__CUDA_ARCH__)
+  return __fdividef(a, b);
+#else
+  return a / b;
+#endif
+}
+PF_HD double pf_div(double a, double b) { return a / b; }
 PF_HD float pf_abs(float x) { return fabsf(x); }
 PF_HD double pf_abs(double x) { return fabs(x); }
 PF_HD float pf_sqrt(float x) { return sqrtf(x); }
@@ -69,8 +79,8 @@ PF_HD void jacobi_pair(T* ap, T* aq, T* vp, T* vq) {
   const T gamma = ap[0] * aq[0] + ap[1] * aq[1] + ap[2] * aq[2];
   const T eps = sizeof(T) == 4 ? (T)1e-14 : (T)1e-30;      // (relative tolerance)^2
   if (!(gamma * gamma > eps * alpha * beta)) return;        // already orthogonal (or NaN / zero)
-  const T zeta = (beta - alpha) / ((T)2 * gamma);
-  const T tt = (zeta >= (T)0 ? (T)1 : (T)-1) / (pf_abs(zeta) + pf_sqrt((T)1 + zeta * zeta));
+  const T zeta = pf_div(beta - alpha, (T)2 * gamma);
+  const T tt = pf_div(zeta >= (T)0 ? (T)1 : (T)-1, pf_abs(zeta) + pf_sqrt((T)1 + zeta * zeta));
   const T c = pf_rsqrt((T)1 + tt * tt);
   const T s = c * tt;
 #pragma unroll
