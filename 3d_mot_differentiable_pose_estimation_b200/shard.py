@@ -8,6 +8,7 @@ Detection/evaluator/FrontEvaluator.py:143).  Gradients stay with the rank that o
 """
 from __future__ import annotations
 
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -30,16 +31,21 @@ def object_range(seq_offsets: torch.Tensor, rank: int, world_size: int) -> Tuple
     return int(seq_offsets[s0]), int(seq_offsets[s1])
 
 
-def gather_poses(local: torch.Tensor, counts: Optional[list] = None, group=None) -> torch.Tensor:
+def gather_poses(local: torch.Tensor, counts: Optional[list] = None, group=None, async_op: bool = False):
     """All-gather per-rank pose records [n_r, 16] into [sum n_r, 16] in rank order.
-    counts: objects per rank when shards are ragged (None = equal shards)."""
+    counts: objects per rank when shards are ragged (None = equal shards).
+    async_op (equal shards only): returns (out, work) right away -- the collective runs on the
+    backend's own stream, ordered after the work already queued on the current stream, so the caller
+    can queue the backward pass next to it and `work.wait()` when the gathered poses are needed."""
     if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
-        return local
+        return (local, None) if async_op else local
     world = dist.get_world_size(group)
     if counts is None:
         out = torch.empty((world * local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
-        dist.all_gather_into_tensor(out, local.contiguous(), group=group)
-        return out
+        work = dist.all_gather_into_tensor(out, local.contiguous(), group=group, async_op=async_op)
+        return (out, work) if async_op else out
+    if async_op:
+        raise ValueError('async_op needs equal shards')
     if len(counts) != world or counts[dist.get_rank(group)] != local.shape[0]:
         raise ValueError('counts must list the shard size of every rank')
     width = max(counts)
@@ -48,3 +54,36 @@ def gather_poses(local: torch.Tensor, counts: Optional[list] = None, group=None)
     out = torch.empty((world * width,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
     dist.all_gather_into_tensor(out, padded, group=group)
     return torch.cat([out[r * width:r * width + counts[r]] for r in range(world)], dim=0)
+
+
+def _parse_cpulist(text: str) -> set:
+    cpus = set()
+    for part in text.strip().split(','):
+        if not part:
+            continue
+        lo, _, hi = part.partition('-')
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_host_to_gpu(device_index: int, sysfs: str = '/sys') -> Optional[int]:
+    """Pin this process to the CPU cores of the NUMA node its GPU hangs off.  One process per GPU
+    stages its crops through pinned host buffers; first-touching those buffers from local cores keeps
+    the 8 concurrent host->device streams off the inter-socket link.  Returns the node, or None when
+    the platform does not say (VMs report numa_node = -1) -- then nothing is changed."""
+    try:
+        props = torch.cuda.get_device_properties(device_index)
+        bus = '%04x:%02x:%02x.0' % (props.pci_domain_id, props.pci_bus_id, props.pci_device_id)
+        with open(os.path.join(sysfs, 'bus/pci/devices', bus, 'numa_node')) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(os.path.join(sysfs, 'devices/system/node/node%d/cpulist' % node)) as f:
+            cpus = _parse_cpulist(f.read())
+        allowed = os.sched_getaffinity(0) & cpus
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except (OSError, ValueError, AttributeError, RuntimeError, AssertionError):
+        return None

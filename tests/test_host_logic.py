@@ -108,6 +108,9 @@ def _gloo_worker(rank, world, port, q):
     s0, s1 = shard.sequence_shard(10, rank, world)
     local = torch.arange(s0 * 4, s1 * 4, dtype=torch.float64)[:, None].repeat(1, 16) + 0.5
     eq = shard.gather_poses(local)
+    eq_async, work = shard.gather_poses(local, async_op=True)      # the form bench.py overlaps with the backward pass
+    work.wait()
+    assert torch.equal(eq_async, eq)
     counts = [3, 5]
     ragged = shard.gather_poses(torch.full((counts[rank], 16), float(rank), dtype=torch.float64), counts=counts)
     q.put((rank, eq[:, 0].tolist(), ragged[:, 0].tolist()))
@@ -129,3 +132,14 @@ def test_gather_poses_world2_gloo():
     for rank, eq, ragged in got:
         assert eq == [i + 0.5 for i in range(40)]                  # rank order, every object exactly once
         assert ragged == [0.0] * 3 + [1.0] * 5
+
+
+def test_numa_binding_helpers(tmp_path):
+    """bind_host_to_gpu parses sysfs cpulists and is a no-op (None) when the platform gives no answer."""
+    import importlib
+    shard = importlib.import_module('3d_mot_differentiable_pose_estimation_b200.shard')
+    assert shard._parse_cpulist('0-3,8,10-11\n') == {0, 1, 2, 3, 8, 10, 11}
+    assert shard._parse_cpulist('') == set()
+    before = os.sched_getaffinity(0)
+    assert shard.bind_host_to_gpu(0, sysfs=str(tmp_path)) is None   # no CUDA device / no sysfs entry here
+    assert os.sched_getaffinity(0) == before
