@@ -147,7 +147,57 @@ class ClockSampler:
     def __init__(self, index=0):
         self.index, self.samples, self.stop, self.th = index, [], False, None
 
+    # NVML clocks-event-reason bits (nvml.h)
+    BITS = {'sw_power_cap': 0x4, 'hw_slowdown': 0x8, 'sw_thermal_slowdown': 0x20, 'hw_thermal_slowdown': 0x40}
+
+    def _run_nvml(self):
+        """NVML in-process: ~1 ms per sample instead of ~100 ms per nvidia-smi call, so even a 0.4 s timed
+        region is covered by tens of samples.  Returns False when NVML is not usable."""
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+            phys = self.index
+            if vis:
+                ids = [v for v in vis.split(',') if v.strip()]
+                if self.index < len(ids) and ids[self.index].strip().isdigit():
+                    phys = int(ids[self.index])
+            h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+            reasons = None
+            for name in ('nvmlDeviceGetCurrentClocksEventReasons', 'nvmlDeviceGetCurrentClocksThrottleReasons'):
+                fn = getattr(pynvml, name, None)
+                if fn is None:
+                    continue
+                try:
+                    int(fn(h))
+                    reasons = fn
+                    break
+                except Exception:
+                    continue
+            if reasons is None:
+                return False
+        except Exception as e:
+            print('bench: NVML clock sampling unavailable (%r), using nvidia-smi' % (e,), file=sys.stderr)
+            return False
+        while not self.stop:
+            try:
+                sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                r = int(reasons(h))
+                self.samples.append([str(sm), str(mx)] + ['Active' if r & self.BITS[k] else 'Not Active' for k in
+                                                         ('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown',
+                                                          'sw_power_cap')])
+            except Exception as e:
+                if not getattr(self, 'warned', False):
+                    self.warned = True
+                    print('bench: NVML sample failed: %r' % (e,), file=sys.stderr)
+            time.sleep(0.005)
+        return True
+
     def _run(self):
+        if self._run_nvml():
+            return
         while not self.stop:
             try:
                 out = subprocess.run(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',

@@ -123,6 +123,31 @@ def test_ransac_fit_vs_oracle(pf, h, w, b, n_hyp, seed):
     print('ransac', (h, w, n_hyp), worst, 'min margin', min(margins))
 
 
+def test_ransac_sparse_masks_vs_oracle(pf):
+    """The fast path's select list (every even-ranked valid pixel + next-set-bit for the odd ranks)
+    against the oracle on masks with long empty runs, odd / tiny counts and a 112x112 crop (1 CTA/SM)."""
+    rng = np.random.default_rng(99)
+    for (h, w, b, n_hyp, seed) in [(64, 64, 12, 64, 51), (112, 112, 4, 32, 52)]:
+        d = pf.synth.make_objects(b, h, w, seed=seed, n_hyp=n_hyp)
+        m = d['mask'].numpy().copy()
+        m[0, 1:h - 1] = 0                            # only the first and last rows: > 100 empty words between them
+        m[1, :, 1:] = 0                              # one column: one valid pixel per row
+        m[2].reshape(-1)[::2] = 0                    # every other pixel
+        keep = rng.choice(h * w, size=h * w - 13, replace=False)
+        m[3].reshape(-1)[keep] = 0                   # 13 scattered pixels at most (odd count)
+        d['mask'] = torch.from_numpy(m)
+        nv = ((d['mask'] != 0) & (d['depth'] > 0)).reshape(b, -1).sum(1).clamp(min=1)
+        idx = (torch.from_numpy(rng.integers(0, 1 << 30, size=(b, n_hyp, 10))) % nv[:, None, None]).to(torch.int32)
+        idx[:, 0, 0] = (nv - 1).to(torch.int32)      # the very last valid point, odd or even rank
+        d['sample_idx'] = idx
+        t = _cuda(d)
+        raw = pf.pose_fit_raw(t['noc'], t['depth'], t['mask'], t['bbox_xy0'], sample_idx=t['sample_idx'])
+        ora = po.batch_pose(d['noc'].numpy(), d['depth'].numpy(), d['mask'].numpy(), d['bbox_xy0'].numpy(),
+                            sample_idx=d['sample_idx'].numpy())
+        worst, n = check_against_oracle(raw, ora, ransac=True)
+        print('sparse ransac', (h, w), worst, n)
+
+
 def test_tma_and_fallback_loaders_agree(pf, monkeypatch):
     d = pf.synth.make_objects(24, 64, 64, seed=21, n_hyp=32)
     t = _cuda(d)
