@@ -148,6 +148,51 @@ def test_ransac_sparse_masks_vs_oracle(pf):
         print('sparse ransac', (h, w), worst, n)
 
 
+def test_ransac_large_crops_global_mode(pf, monkeypatch):
+    """Boxes too large for the shared-memory staging (the reference takes any bbox up to the 240x320
+    frame, pose_estimation.py:256-267) run the RANSAC kernel in its global-memory mode: against the
+    oracle on 120x160 and frame-sized crops, and bit-identical masks/winners vs the staged mode on 64x64."""
+    for (h, w, b, n_hyp, seed) in [(120, 160, 3, 48, 61), (240, 320, 2, 24, 62), (117, 131, 2, 16, 63)]:
+        d = pf.synth.make_objects(b, h, w, seed=seed, n_hyp=n_hyp, align_x0=1 if w % 4 else 4)
+        t = _cuda(d)
+        raw = pf.pose_fit_raw(t['noc'], t['depth'], t['mask'], t['bbox_xy0'], sample_idx=t['sample_idx'])
+        ora = po.batch_pose(d['noc'].numpy(), d['depth'].numpy(), d['mask'].numpy(), d['bbox_xy0'].numpy(),
+                            sample_idx=d['sample_idx'].numpy())
+        worst, n = check_against_oracle(raw, ora, ransac=True)
+        print('large ransac', (h, w), worst, n)
+    d = pf.synth.make_objects(16, 64, 64, seed=64, n_hyp=64)
+    t = _cuda(d)
+    a = pf.pose_fit_raw(t['noc'], t['depth'], t['mask'], t['bbox_xy0'], sample_idx=t['sample_idx'])
+    monkeypatch.setenv('POSEFIT_RANSAC_GLOBAL', '1')
+    g = pf.pose_fit_raw(t['noc'], t['depth'], t['mask'], t['bbox_xy0'], sample_idx=t['sample_idx'])
+    torch.cuda.synchronize()
+    assert torch.equal(a.inlier_mask, g.inlier_mask) and torch.equal(a.winner, g.winner)
+    assert torch.equal(a.status, g.status)
+    assert float((a.pose[:, :13] - g.pose[:, :13]).abs().max()) < 1e-10
+    # points mode beyond the staged capacity (49 B per point): 20 000 correspondences per object
+    rng = np.random.default_rng(65)
+    n, n_hyp = 20000, 32
+    src = rng.uniform(-0.5, 0.5, size=(2, n, 3))
+    dst = np.empty_like(src)
+    idx = rng.integers(0, n, size=(2, n_hyp, 10)).astype(np.int32)
+    for i in range(2):
+        rot = np.linalg.qr(rng.normal(size=(3, 3)))[0]
+        dst[i] = 1.3 * src[i] @ rot.T + np.array([0.1, 0.2, -3.0]) + rng.normal(scale=0.01, size=(n, 3))
+        bad = rng.uniform(size=n) < 0.1
+        dst[i, bad, 2] -= rng.uniform(25, 40, size=bad.sum())
+    monkeypatch.delenv('POSEFIT_RANSAC_GLOBAL')
+    rans = pf.points_fit_raw(torch.from_numpy(np.ascontiguousarray(src.transpose(0, 2, 1))).cuda(),
+                             torch.from_numpy(np.ascontiguousarray(dst.transpose(0, 2, 1))).cuda(),
+                             None, sample_idx=torch.from_numpy(idx).cuda())
+    for i in range(2):
+        o = po.similarity_transform(src[i], dst[i], idx[i])
+        assert o['ok'] and int(rans.status[i]) == 0
+        want = np.zeros(n, dtype=np.uint8)
+        want[o['inlier_idx']] = 1
+        np.testing.assert_array_equal(rans.inlier_mask[i].cpu().numpy(), want)
+        assert rot_err_deg(rans.pose[i, 1:10].cpu().numpy().reshape(3, 3), o['rot_t'].T) < 1e-7
+
+
 def test_tma_and_fallback_loaders_agree(pf, monkeypatch):
     d = pf.synth.make_objects(24, 64, 64, seed=21, n_hyp=32)
     t = _cuda(d)
