@@ -367,17 +367,44 @@ def run_ours(args):
     h2d = sum(v.numel() * v.element_size() for v in host.values()) + sum(v.numel() * v.element_size() for v in hg.values())
     d2h = out_host.numel() * 4
 
+    # Two-stage pipeline, the way a data loader feeds a training step: the inputs of step i+1 cross
+    # PCIe on a copy stream while step i computes.  Every step still copies ALL of its inputs from
+    # pinned host memory and reads its result back; two device buffer sets, guarded by events.
+    copy_stream = torch.cuda.Stream()
+    slots = [{'ready': torch.cuda.Event(), 'free': torch.cuda.Event()} for _ in range(2)]
+    for sl in slots:
+        sl['free'].record()
+    state = {'i': 0}
+
+    def e2e_upload(sl):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(sl['free'])                   # the step that last used this set is done
+            sl['noc'] = host['noc'].to(dev, non_blocking=True)
+            sl['depth'] = host['depth'].to(dev, non_blocking=True)
+            sl['mask'] = host['mask'].to(dev, non_blocking=True)
+            sl['xy0'] = host['bbox_xy0'].to(dev, non_blocking=True)
+            sl['g'] = tuple(hg[k].to(dev, non_blocking=True) for k in ('s', 'R', 't'))
+            sl['ready'].record()
+
     def e2e_step():
-        noc = host['noc'].to(dev, non_blocking=True).requires_grad_(True)
-        depth = host['depth'].to(dev, non_blocking=True)
-        mask = host['mask'].to(dev, non_blocking=True)
-        xy0 = host['bbox_xy0'].to(dev, non_blocking=True)
-        gs, gR, gt = (hg[k].to(dev, non_blocking=True) for k in ('s', 'R', 't'))
-        scale, rot, trans, _, _, _ = pf.pose_fit(noc, depth, mask, xy0, kinv)
+        cur = torch.cuda.current_stream()
+        sl = slots[state['i'] % 2]
+        if 'noc' not in sl or state['i'] == 0:
+            e2e_upload(sl)                                       # first step: nothing was prefetched
+        nxt = slots[(state['i'] + 1) % 2]
+        cur.wait_event(sl['ready'])
+        e2e_upload(nxt)                                          # next step's inputs, behind this step's compute
+        noc = sl['noc'].requires_grad_(True)
+        for t in (sl['noc'], sl['depth'], sl['mask'], sl['xy0']) + sl['g']:
+            t.record_stream(cur)
+        gs, gR, gt = sl['g']
+        scale, rot, trans, _, _, _ = pf.pose_fit(noc, sl['depth'], sl['mask'], sl['xy0'], kinv)
         loss = (scale * gs).sum() + (rot * gR).sum() + (trans * gt).sum()
         loss.backward()
         out_host.copy_(torch.cat([scale.detach()[:, None], rot.detach().reshape(ne, 9), trans.detach()], dim=1),
                        non_blocking=True)
+        sl['free'].record(cur)
+        state['i'] += 1
         return noc.grad
 
     for _ in range(max(args.warmup, 3)):
@@ -390,6 +417,7 @@ def run_ours(args):
     t0.record()
     for _ in range(k_e2e):
         e2e_step()
+    torch.cuda.current_stream().wait_stream(copy_stream)         # every upload issued in the region ends in it
     t1.record()
     torch.cuda.synchronize()
     e2e_ms = t0.elapsed_time(t1) / k_e2e
