@@ -38,7 +38,7 @@ class PoseFitError(RuntimeError):
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile csrc/ for sm_100a into libposefit_b200.so (no GPU needed)."""
     src_time = max(os.path.getmtime(os.path.join(CSRC, f)) for f in os.listdir(CSRC)
-                   if f.endswith(('.cu', '.h', 'Makefile')))
+                   if f.endswith(('.cu', '.cuh', '.h', 'Makefile')))
     inc = os.path.join(os.path.dirname(_HERE), 'include', 'posefit.h')
     if os.path.exists(inc):
         src_time = max(src_time, os.path.getmtime(inc))

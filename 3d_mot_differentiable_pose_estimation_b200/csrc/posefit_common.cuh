@@ -1,0 +1,355 @@
+// posefit_common.cuh -- PTX helpers (mbarrier, TMA bulk copy, cp.async), launch parameters, tile loaders/views, block reduction
+// Part of libposefit_b200.so: included by posefit_kernels.cu (one translation unit, so every kernel sees the
+// same inlined helpers and the build stays a single nvcc call).  See include/posefit.h for the C ABI.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdlib.h>
+
+#include "posefit.h"
+#include "posefit_math.h"
+
+namespace posefit {
+
+constexpr int kAccPlain = 17;     // n, sx3, sy3, syx9, sxx
+constexpr int kAccRansac = 23;    // n, sx3, sy3, syx9, sxx6 (xx,xy,xz,yy,yz,zz), syy
+
+// ---------------------------------------------------------------------------------------------
+// PTX helpers: mbarrier + 1-D TMA bulk copy (SASS: UBLKCP, SYNCS)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a lost copy traps (kernel error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// launch parameters
+// ---------------------------------------------------------------------------------------------
+struct FwdParams {
+  const float* noc;
+  const float* depth;
+  const uint8_t* mask;
+  const int32_t* bbox;
+  const double* kinv;
+  const int32_t* sample_idx;
+  const double* src_pts;        // points mode: [B][3][P] float64 source (already centred NOC)
+  const double* dst_pts;        // points mode: [B][3][P] float64 target
+  double* pose;
+  double* ctx;
+  int32_t* status;
+  int32_t* n_valid;
+  uint8_t* inlier_mask;
+  int32_t* winner;
+  double ratio_adapt;
+  double pass_override, stop_override;   // > 0: use instead of the data-derived PassT / StopT (getRANSACInliers' arguments)
+  int kinv_per_object;
+  int B, H, W, P;
+  int n_hyp, n_samp, ref_compat;
+  int no_fast;                  // debugging: force the generic per-pixel passes of the RANSAC kernel
+  int global_tile;              // RANSAC kernel: crop too large for shared memory, passes read global memory
+  int tile_px, tiles_per_obj;   // a tile = tile_px consecutive pixels (whole rows in crop mode)
+  int n_stages, tma_ok;
+  int early_dep;                // bit k: kernel k of the chain signals its dependents before its own wait
+  int prewarm;                  // K-solve kernels: run a warm-up pass before griddepcontrol.wait (small grids)
+  int n_words;                  // ceil(P / 32)
+  uint32_t w_magic;             // ceil(2^32 / W): px / W == __umulhi(px, w_magic) for px, W < 65536
+  // plain path (K-moments / K-solve)
+  double* ws;                   // [B][max_parts][17] partial moments
+  long long total_chunks;
+  int chunks_per_obj, chunks_per_warp, max_parts, vec_ok;
+  uint32_t warp_smem_bytes;     // per-warp shared memory: cp.async ring + ray tables
+  // shared-memory carve-up (bytes from the dynamic smem base)
+  uint32_t off_geom, off_tables, off_red, off_bits, off_prefix, off_stats, off_res, off_tf, off_stages;
+  uint32_t stage_bytes, st_depth, st_mask, st_idx;   // offsets inside one stage
+};
+
+// Per-object geometry (K^-1 and the crop origin) lives in shared memory, double buffered: the
+// record of object j+1 is fetched with cp.async (LDGSTS, no register staging) while object j is
+// being processed.
+struct GeomSmem {
+  double k[9];
+  int xy0[2];
+};
+
+struct ObjGeom {
+  const double* k;   // -> shared
+  double k0, k2, k4, k5;
+  int x0, y0;
+  bool simple;
+};
+
+__device__ __forceinline__ void cp_async_8(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_4(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// threads 0..10 request the geometry record of `obj` into `dst`
+__device__ __forceinline__ void fetch_geom(const FwdParams& p, int obj, GeomSmem* dst, int tid) {
+  if (tid < 9) cp_async_8(&dst->k[tid], p.kinv + (p.kinv_per_object ? 9 * (size_t)obj : 0) + tid);
+  else if (tid < 11) cp_async_4(&dst->xy0[tid - 9], p.bbox + 2 * (size_t)obj + (tid - 9));
+  cp_async_commit();
+}
+
+// after cp_async_wait_all by the fetching threads + __syncthreads
+__device__ __forceinline__ void read_geom(const GeomSmem* src, ObjGeom& g) {
+  g.k = src->k;
+  g.k0 = src->k[0]; g.k2 = src->k[2]; g.k4 = src->k[4]; g.k5 = src->k[5];
+  g.x0 = src->xy0[0];
+  g.y0 = src->xy0[1];
+  g.simple = (src->k[1] == 0.0 && src->k[3] == 0.0 && src->k[6] == 0.0 && src->k[7] == 0.0 && src->k[8] == 1.0);
+}
+
+// Camera-space point of frame pixel (x0+col, y0+row) at depth zd, pose_estimation.py:34-41:
+// K^-1 [u v 1]^T scaled to depth, y and z negated.  `simple` = pinhole K without skew, where
+// the third ray component is exactly 1 and the per-column / per-row ray tables are used.
+__device__ __forceinline__ void backproject_px(const ObjGeom& g, const double* rxc, const double* ryr, int row, int col,
+                                               double zd, double& y0, double& y1, double& y2) {
+  if (g.simple) {
+    y0 = rxc[col] * zd;
+    y1 = -(ryr[row] * zd);
+    y2 = -zd;
+  } else {
+    const double u = (double)(g.x0 + col), v = (double)(g.y0 + row);
+    const double X = g.k[0] * u + g.k[1] * v + g.k[2];
+    const double Y = g.k[3] * u + g.k[4] * v + g.k[5];
+    const double Z = g.k[6] * u + g.k[7] * v + g.k[8];
+    y0 = X * zd / Z;
+    y1 = -(Y * zd / Z);
+    y2 = -(Z * zd / Z);
+  }
+}
+
+__device__ __forceinline__ void build_ray_tables(const FwdParams& p, const ObjGeom& g, double* rxc, double* ryr, int tid,
+                                                 int nt) {
+  for (int i = tid; i < p.W; i += nt) rxc[i] = g.k0 * (double)(g.x0 + i) + g.k2;
+  for (int i = tid; i < p.H; i += nt) ryr[i] = g.k4 * (double)(g.y0 + i) + g.k5;
+}
+
+// Issue the copies of one tile (pixels [i0, i0+npx) of object obj; idx too when with_idx).
+// Called by ONE thread.  Crop-mode stage layout: noc plane c at c*npx floats, depth at st_depth,
+// mask at st_mask, sample indices at st_idx.  Points mode: src plane c at c*npx doubles, dst
+// planes at st_depth, mask at st_mask.
+template <bool POINTS>
+__device__ __forceinline__ void issue_tile(const FwdParams& p, unsigned char* stage, uint64_t* bar, int obj, int i0,
+                                           int npx_i, bool with_idx) {
+  const uint32_t npx = (uint32_t)npx_i;
+  const size_t base = (size_t)obj * p.P + (size_t)i0;
+  const uint32_t idx_bytes = with_idx ? (uint32_t)p.n_hyp * p.n_samp * 4u : 0u;
+  fence_proxy_async();
+  mbar_expect_tx(bar, npx * (POINTS ? 49u : 17u) + idx_bytes);
+  if (POINTS) {
+    if (npx_i == p.P) {
+      bulk_g2s(stage, p.src_pts + (size_t)obj * 3 * p.P, npx * 24u, bar);
+      bulk_g2s(stage + p.st_depth, p.dst_pts + (size_t)obj * 3 * p.P, npx * 24u, bar);
+    } else {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        bulk_g2s(stage + (size_t)c * npx * 8, p.src_pts + ((size_t)obj * 3 + c) * p.P + i0, npx * 8u, bar);
+        bulk_g2s(stage + p.st_depth + (size_t)c * npx * 8, p.dst_pts + ((size_t)obj * 3 + c) * p.P + i0, npx * 8u, bar);
+      }
+    }
+  } else {
+    if (npx_i == p.P) {
+      bulk_g2s(stage, p.noc + (size_t)obj * 3 * p.P, npx * 12u, bar);
+    } else {
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+        bulk_g2s(stage + (size_t)c * npx * 4, p.noc + ((size_t)obj * 3 + c) * p.P + i0, npx * 4u, bar);
+    }
+    bulk_g2s(stage + p.st_depth, p.depth + base, npx * 4u, bar);
+  }
+  bulk_g2s(stage + p.st_mask, p.mask + base, npx, bar);
+  if (with_idx) bulk_g2s(stage + p.st_idx, p.sample_idx + (size_t)obj * p.n_hyp * p.n_samp, idx_bytes, bar);
+}
+
+// Fallback loader for shapes/pointers the bulk copy cannot take (16-byte rules): all threads copy.
+template <bool POINTS>
+__device__ __forceinline__ void load_tile_generic(const FwdParams& p, unsigned char* stage, int obj, int i0, int npx,
+                                                  bool with_idx, int tid, int nt) {
+  const size_t base = (size_t)obj * p.P + (size_t)i0;
+  uint8_t* smsk = stage + p.st_mask;
+  if (POINTS) {
+    double* ssrc = reinterpret_cast<double*>(stage);
+    double* sdst = reinterpret_cast<double*>(stage + p.st_depth);
+    for (int i = tid; i < npx; i += nt) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        ssrc[c * npx + i] = p.src_pts[((size_t)obj * 3 + c) * p.P + i0 + i];
+        sdst[c * npx + i] = p.dst_pts[((size_t)obj * 3 + c) * p.P + i0 + i];
+      }
+      smsk[i] = p.mask[base + i];
+    }
+  } else {
+    float* snoc = reinterpret_cast<float*>(stage);
+    float* sdep = reinterpret_cast<float*>(stage + p.st_depth);
+    for (int i = tid; i < npx; i += nt) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) snoc[c * npx + i] = p.noc[((size_t)obj * 3 + c) * p.P + i0 + i];
+      sdep[i] = p.depth[base + i];
+      smsk[i] = p.mask[base + i];
+    }
+  }
+  if (with_idx) {
+    int32_t* sidx = reinterpret_cast<int32_t*>(stage + p.st_idx);
+    const int n = p.n_hyp * p.n_samp;
+    for (int i = tid; i < n; i += nt) sidx[i] = p.sample_idx[(size_t)obj * n + i];
+  }
+}
+
+// Uniform view of the correspondences held in one stage.
+//   crop mode  : x = noc - 0.5 (pose_estimation.py:323), y = back-projected depth (:34-41),
+//                valid = mask & depth > 0 (:23-25)
+//   points mode: x, y given explicitly (the [4,N] arrays of pose_utils.py), valid = mask
+template <bool POINTS>
+struct TileView {
+  const float* noc;
+  const float* dep;
+  const double* src;
+  const double* dst;
+  const uint8_t* msk;
+  int npx;
+  __device__ __forceinline__ TileView(const FwdParams& p, const unsigned char* stage, int npx_) : npx(npx_) {
+    noc = reinterpret_cast<const float*>(stage);
+    dep = reinterpret_cast<const float*>(stage + p.st_depth);
+    src = reinterpret_cast<const double*>(stage);
+    dst = reinterpret_cast<const double*>(stage + p.st_depth);
+    msk = stage + p.st_mask;
+  }
+  // Large-crop mode of the RANSAC kernel: the same view straight over the object's arrays in global
+  // memory (the crop does not fit in shared memory; the passes re-read it through L2).
+  __device__ __forceinline__ TileView(const FwdParams& p, int obj) : npx(p.P) {
+    noc = p.noc + (size_t)obj * 3 * p.P;
+    dep = p.depth + (size_t)obj * p.P;
+    src = p.src_pts + (size_t)obj * 3 * p.P;
+    dst = p.dst_pts + (size_t)obj * 3 * p.P;
+    msk = p.mask + (size_t)obj * p.P;
+  }
+  __device__ __forceinline__ bool valid(int i, float& z) const {
+    if (POINTS) { z = 1.0f; return msk[i] != 0; }
+    z = dep[i];
+    return msk[i] != 0 && z > 0.0f;
+  }
+  __device__ __forceinline__ void xy(int i, float z, const ObjGeom& g, const double* rxc, const double* ryr, int row,
+                                     int col, double& x0, double& x1, double& x2, double& y0, double& y1,
+                                     double& y2) const {
+    if (POINTS) {
+      x0 = src[i]; x1 = src[npx + i]; x2 = src[2 * npx + i];
+      y0 = dst[i]; y1 = dst[npx + i]; y2 = dst[2 * npx + i];
+    } else {
+      x0 = (double)noc[i] - 0.5;
+      x1 = (double)noc[npx + i] - 0.5;
+      x2 = (double)noc[2 * npx + i] - 0.5;
+      backproject_px(g, rxc, ryr, row, col, (double)z, y0, y1, y2);
+    }
+  }
+};
+
+// Sum v[0..N) over the block (N <= 24).  red: [nwarps][24] doubles.  Result in out[0..N) (shared),
+// valid after the NEXT __syncthreads of the caller.
+// Warp stage: instead of a 5-step butterfly per value (5 N shuffles) the two lanes of a pair SPLIT the
+// remaining values between them at offsets 16, 8 and 4 (24 -> 12 -> 6 -> 3 values per lane), and only
+// the last 3 values go through the two remaining butterfly steps: 27 fp64 shuffles instead of 5 N.
+// Afterwards lane L (L % 4 == 0) holds the warp totals of values 12 b4 + 6 b3 + 3 b2 + {0,1,2}.
+template <int HALF>
+__device__ __forceinline__ void split_step(double (&w)[24], bool up, int offset) {
+#pragma unroll
+  for (int i = 0; i < HALF; ++i) {
+    const double keep = up ? w[HALF + i] : w[i];
+    const double send = up ? w[i] : w[HALF + i];
+    w[i] = keep + __shfl_xor_sync(0xffffffffu, send, offset);
+  }
+}
+
+template <int N, int NT>
+__device__ __forceinline__ void block_reduce(double (&v)[N], double* red, double* out, int tid) {
+  static_assert(N <= 24, "block_reduce: at most 24 values");
+  const int lane = tid & 31, warp = tid >> 5;
+  double w[24];
+#pragma unroll
+  for (int i = 0; i < 24; ++i) w[i] = i < N ? v[i] : 0.0;
+  split_step<12>(w, (lane & 16) != 0, 16);
+  split_step<6>(w, (lane & 8) != 0, 8);
+  split_step<3>(w, (lane & 4) != 0, 4);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    w[i] += __shfl_xor_sync(0xffffffffu, w[i], 2);
+    w[i] += __shfl_xor_sync(0xffffffffu, w[i], 1);
+  }
+  if ((lane & 3) == 0) {
+    double* dst = red + warp * 24 + ((lane >> 4) & 1) * 12 + ((lane >> 3) & 1) * 6 + ((lane >> 2) & 1) * 3;
+    dst[0] = w[0]; dst[1] = w[1]; dst[2] = w[2];
+  }
+  __syncthreads();
+  if (tid < N) {
+    double s = 0.0;
+#pragma unroll
+    for (int wi = 0; wi < NT / 32; ++wi) s += red[wi * 24 + tid];
+    out[tid] = s;
+  }
+}
+
+// Write one object's outputs (include/posefit.h: pose[16], ctx[32], status, n_valid).
+__device__ __forceinline__ void write_pose(const FwdParams& p, int obj, const Fit& f, int status, double n_fit,
+                                           double ratio, double pass_t, double n_valid) {
+  double* po = p.pose + (size_t)obj * POSEFIT_POSE_DOUBLES;
+  po[0] = f.s;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) po[1 + i] = f.R[i];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) po[10 + i] = f.t[i];
+  po[13] = (status == PF_OK) ? n_fit : 0.0;
+  po[14] = ratio;
+  po[15] = pass_t;
+  double* cx = p.ctx + (size_t)obj * POSEFIT_CTX_DOUBLES;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) cx[i] = f.R[i];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) { cx[9 + i] = f.Linv[i]; cx[15 + i] = f.H[i]; }
+  cx[21] = f.s;
+  cx[22] = f.var;
+  cx[23] = (status == PF_OK) ? n_fit : 0.0;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) { cx[24 + i] = f.mux[i]; cx[27 + i] = f.muy[i]; }
+  cx[30] = 0.0;
+  cx[31] = 0.0;
+  p.status[obj] = status;
+  p.n_valid[obj] = (int)n_valid;
+}
+
+}  // namespace posefit
