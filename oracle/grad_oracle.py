@@ -1,9 +1,11 @@
-"""Gradient oracle -- TEST INFRASTRUCTURE.  PARITY UNPINNED: the reference never
-back-propagates through the pose fit (it detaches the NOC patch first,
-Detection/tracker/postprocess.py:151, and returns via torch.from_numpy, :162-165), so there
-is no reference gradient to match.  This is a float64 torch transcription of
-estimateSimilarityUmeyama (PoseEst/pose_utils.py:16-61) whose FORWARD is checked against
-the NumPy oracle on every test input and whose gradients come from torch autograd.
+"""Gradient oracle -- TEST INFRASTRUCTURE.  The reference never back-propagates through the pose
+fit (it detaches the NOC patch first, Detection/tracker/postprocess.py:151, and returns via
+torch.from_numpy, :162-165), so there is no reference gradient to copy.  This is a float64 torch
+transcription of estimateSimilarityUmeyama (PoseEst/pose_utils.py:16-61) whose gradients come
+from torch autograd.  It is PINNED two ways: its forward is checked against the NumPy oracle on
+every test input, and its gradients against central finite differences of the REAL reference
+functions (tests/golden/grad_fd.npz, written by oracle/gen_golden_grad.py;
+tests/test_math_host.py::test_gradients_match_reference_finite_differences).
 """
 from __future__ import annotations
 

@@ -2,8 +2,9 @@
 reference and against the NumPy oracle on seeded synthetic inputs.
 
 Tolerances (BASELINE.json north_star): inlier masks bit-exact, rotation <= 1e-3 degrees,
-translation and scale <= 1e-5 relative, gradients <= 1e-4 relative (vs the autograd
-restatement -- gradient parity is unpinned, the reference has no backward)."""
+translation and scale <= 1e-5 relative, gradients <= 1e-4 relative -- vs central finite differences
+of the real reference functions on the committed small crops (tests/golden/grad_fd.npz) and vs the
+fp64 autograd restatement (itself pinned to those vectors) at full crop sizes."""
 import os
 
 import numpy as np
@@ -364,6 +365,35 @@ def test_backward_vs_autograd_oracle(pf, h, w, with_ransac):
         want_z[rows - y0, cols - x0] = gz
         errz = np.abs(g_depth[i] - want_z).max() / max(np.abs(want_z).max(), 1e-30)
         assert errz <= GRAD_TOL, (i, errz)
+
+
+def test_backward_vs_reference_finite_differences(pf, golden_dir):
+    """The CUDA backward kernel against central finite differences of the REAL reference functions
+    (tests/golden/grad_fd.npz, oracle/gen_golden_grad.py): gradients w.r.t. every NOC value and every
+    depth value of the crop, tolerance 1e-4 relative (north_star); exact zeros on pixels outside the fit."""
+    g = np.load(os.path.join(golden_dir, 'grad_fd.npz'))
+    worst = 0.0
+    for k in range(int(g['n_cases'])):
+        noc = torch.from_numpy(g[f'noc_{k}'])[None].cuda().requires_grad_(True)
+        depth = torch.from_numpy(g[f'depth_{k}'])[None].cuda().requires_grad_(True)
+        mask = torch.from_numpy(g[f'mask_{k}'])[None].cuda()
+        xy0 = torch.from_numpy(g[f'xy0_{k}'])[None].cuda()
+        scale, rot, trans, _, status, n_valid = pf.pose_fit(noc, depth, mask, xy0)
+        assert int(status[0]) == 0 and int(n_valid[0]) == int(g[f'n_valid_{k}'])
+        np.testing.assert_allclose(float(scale[0].detach()), float(g[f's_{k}']), rtol=1e-5)
+        assert rot_err_deg(rot[0].detach().cpu().numpy().astype(np.float64), g[f'R_{k}']) <= ROT_TOL_DEG
+        loss = (scale[0] * float(g[f'g_s_{k}']) + (rot[0] * torch.from_numpy(g[f'g_R_{k}']).cuda().to(rot.dtype)).sum() +
+                (trans[0] * torch.from_numpy(g[f'g_t_{k}']).cuda().to(trans.dtype)).sum())
+        loss.backward()
+        got_n, got_z = noc.grad[0].cpu().numpy().astype(np.float64), depth.grad[0].cpu().numpy().astype(np.float64)
+        want_n, want_z = g[f'grad_noc_{k}'], g[f'grad_depth_{k}']
+        e_n = np.abs(got_n - want_n).max() / np.abs(want_n).max()
+        e_z = np.abs(got_z - want_z).max() / np.abs(want_z).max()
+        worst = max(worst, e_n, e_z)
+        assert e_n <= GRAD_TOL and e_z <= GRAD_TOL, (k, e_n, e_z)
+        invalid = (g[f'mask_{k}'] == 0) | (g[f'depth_{k}'] <= 0)
+        assert np.all(got_n[:, invalid] == 0.0) and np.all(got_z[invalid] == 0.0)
+    print('backward vs reference finite differences: worst relative error', worst)
 
 
 def test_full_size_properties(pf):

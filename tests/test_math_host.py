@@ -158,3 +158,49 @@ def test_adjoint_matches_autograd(lib):
         my_gy = (xt @ GC.T + gmuy) / n
         np.testing.assert_allclose(my_gx, gx.numpy(), rtol=1e-8, atol=1e-10 * np.abs(gx.numpy()).max())
         np.testing.assert_allclose(my_gy, gy.numpy(), rtol=1e-8, atol=1e-10 * np.abs(gy.numpy()).max())
+
+
+def _fd_case(g, k):
+    """One case of tests/golden/grad_fd.npz -> correspondences in np.where order + the FD gradients at them."""
+    noc, depth, mask, xy0 = g[f'noc_{k}'], g[f'depth_{k}'], g[f'mask_{k}'], g[f'xy0_{k}']
+    h, w = depth.shape
+    x0, y0 = int(xy0[0]), int(xy0[1])
+    frame_d = np.zeros((po.FRAME_H, po.FRAME_W), dtype=np.float32)
+    frame_m = np.zeros((po.FRAME_H, po.FRAME_W), dtype=bool)
+    frame_d[y0:y0 + h, x0:x0 + w] = depth
+    frame_m[y0:y0 + h, x0:x0 + w] = mask != 0
+    k_mat = po.motfront_intrinsics()
+    noc_pts, depth_pts, (rows, cols) = po.crop_correspondences(np.transpose(noc, (1, 2, 0)), frame_d, frame_m,
+                                                               (x0, y0, x0 + w, y0 + h), k_mat)
+    want_x = g[f'grad_noc_{k}'][:, rows - y0, cols - x0].T               # [N,3]
+    want_z = g[f'grad_depth_{k}'][rows - y0, cols - x0]                  # [N]
+    rx = (cols - k_mat[0, 2]) / k_mat[0, 0]
+    ry = (rows - k_mat[1, 2]) / k_mat[1, 1]
+    return noc_pts, depth_pts, want_x, want_z, rx, ry
+
+
+def test_gradients_match_reference_finite_differences(lib, golden_dir):
+    """PINS the gradient path: tests/golden/grad_fd.npz holds central finite differences of the REAL
+    reference functions (backproject + estimateSimilarityUmeyama, oracle/gen_golden_grad.py).  Both the
+    autograd restatement and the host-compiled adjoint of csrc/posefit_math.h must reproduce them
+    (FD accuracy ~1e-8 relative: tolerance 2e-6 of the largest component)."""
+    g = np.load(os.path.join(golden_dir, 'grad_fd.npz'))
+    for k in range(int(g['n_cases'])):
+        noc_pts, depth_pts, want_x, want_z, rx, ry = _fd_case(g, k)
+        n = noc_pts.shape[0]
+        assert n == int(g[f'n_valid_{k}'])
+        gs, gR, gt = float(g[f'g_s_{k}']), g[f'g_R_{k}'], g[f'g_t_{k}']
+        gx, gy, (s, R, t) = grad_oracle.fit_gradients(torch.from_numpy(noc_pts), torch.from_numpy(depth_pts), None,
+                                                      gs, torch.from_numpy(gR), torch.from_numpy(gt))
+        np.testing.assert_allclose(float(s), float(g[f's_{k}']), rtol=1e-12)
+        np.testing.assert_allclose(R.numpy(), g[f'R_{k}'], atol=1e-12)
+        out = np.zeros(16)
+        srcc, dstc, gRc, gtc = (np.ascontiguousarray(a) for a in (noc_pts, depth_pts, gR, gt))
+        lib.pf_check_adjoint(_dp(srcc), _dp(dstc), ctypes.c_int(n), ctypes.c_double(gs), _dp(gRc), _dp(gtc), _dp(out))
+        GC, gvar, gmux, gmuy = out[:9].reshape(3, 3), out[9], out[10:13], out[13:16]
+        xt, yt = noc_pts - noc_pts.mean(0), depth_pts - depth_pts.mean(0)
+        for name, got_x, got_y in (('autograd restatement', gx.numpy(), gy.numpy()),
+                                   ('posefit_math.h adjoint', (yt @ GC + 2 * gvar * xt + gmux) / n, (xt @ GC.T + gmuy) / n)):
+            got_z = got_y[:, 0] * rx - got_y[:, 1] * ry - got_y[:, 2]    # y = (rx z, -ry z, -z), pose_estimation.py:34-41
+            assert np.abs(got_x - want_x).max() <= 2e-6 * np.abs(want_x).max(), (name, k)
+            assert np.abs(got_z - want_z).max() <= 2e-6 * np.abs(want_z).max(), (name, k)
