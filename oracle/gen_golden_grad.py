@@ -61,8 +61,10 @@ def make_case(rng, h, w, x0, y0, fill):
     return noc, depth, mask.astype(np.uint8), np.array([x0, y0], dtype=np.int32)
 
 
-def probe(pu, pe, noc, depth, mask, xy0, g_s, g_r, g_t):
-    """L(noc, depth) through the real reference functions; noc [h,w,3], depth [h,w] float64."""
+def probe(pu, pe, noc, depth, mask, xy0, g_s, g_r, g_t, sample_idx=None):
+    """L(noc, depth) through the real reference functions; noc [h,w,3], depth [h,w] float64.
+    sample_idx [n_hyp,10]: go through estimateSimilarityTransform (RANSAC, pose_utils.py:86-117) with the
+    indices replayed instead of the plain fit."""
     h, w = depth.shape
     x0, y0 = int(xy0[0]), int(xy0[1])
     depth_pad = np.zeros((po.FRAME_H, po.FRAME_W))                               # pose_estimation.py:260-262
@@ -73,16 +75,20 @@ def probe(pu, pe, noc, depth, mask, xy0, g_s, g_r, g_t):
     nocs_pad[y0:y0 + h, x0:x0 + w, :] = noc
     pts, idxs = pe.backproject(depth_pad, po.motfront_intrinsics(), mask_pad)   # :290
     noc_pts = nocs_pad[idxs[0], idxs[1], :] - 0.5                                # :323
-    scales, rotation, translation, _ = pu.estimateSimilarityUmeyama(_hom(noc_pts), _hom(pts))
+    if sample_idx is None:
+        scales, rotation, translation, _ = pu.estimateSimilarityUmeyama(_hom(noc_pts), _hom(pts))
+    else:
+        with ref_import.replay_randint(sample_idx, pu):
+            scales, rotation, translation, _ = pu.estimateSimilarityTransform(noc_pts, pts)
     s, rot, t = scales[0], rotation.T, translation                               # Rotation is R^T (pose_utils.py:44)
     return g_s * s + float((g_r * rot).sum()) + float((g_t * t).sum()), (s, rot, t), int(pts.shape[0])
 
 
-def finite_differences(pu, pe, noc32, depth32, mask, xy0, g_s, g_r, g_t):
+def finite_differences(pu, pe, noc32, depth32, mask, xy0, g_s, g_r, g_t, sample_idx=None):
     noc = noc32.astype(np.float64)
     depth = depth32.astype(np.float64)
     h, w = depth.shape
-    _, fwd, n_valid = probe(pu, pe, noc, depth, mask, xy0, g_s, g_r, g_t)
+    _, fwd, n_valid = probe(pu, pe, noc, depth, mask, xy0, g_s, g_r, g_t, sample_idx)
     valid = (mask != 0) & (depth > 0)
     g_noc = np.zeros((h, w, 3))
     g_depth = np.zeros((h, w))
@@ -94,13 +100,13 @@ def finite_differences(pu, pe, noc32, depth32, mask, xy0, g_s, g_r, g_t):
                 p, m = noc.copy(), noc.copy()
                 p[i, j, c] += STEP
                 m[i, j, c] -= STEP
-                g_noc[i, j, c] = (probe(pu, pe, p, depth, mask, xy0, g_s, g_r, g_t)[0] -
-                                  probe(pu, pe, m, depth, mask, xy0, g_s, g_r, g_t)[0]) / (2 * STEP)
+                g_noc[i, j, c] = (probe(pu, pe, p, depth, mask, xy0, g_s, g_r, g_t, sample_idx)[0] -
+                                  probe(pu, pe, m, depth, mask, xy0, g_s, g_r, g_t, sample_idx)[0]) / (2 * STEP)
             p, m = depth.copy(), depth.copy()
             p[i, j] += STEP
             m[i, j] -= STEP
-            g_depth[i, j] = (probe(pu, pe, noc, p, mask, xy0, g_s, g_r, g_t)[0] -
-                             probe(pu, pe, noc, m, mask, xy0, g_s, g_r, g_t)[0]) / (2 * STEP)
+            g_depth[i, j] = (probe(pu, pe, noc, p, mask, xy0, g_s, g_r, g_t, sample_idx)[0] -
+                             probe(pu, pe, noc, m, mask, xy0, g_s, g_r, g_t, sample_idx)[0]) / (2 * STEP)
     return g_noc, g_depth, fwd, n_valid
 
 
@@ -122,6 +128,29 @@ def main():
         out[f'grad_depth_{k}'] = g_depth
         out[f's_{k}'], out[f'R_{k}'], out[f't_{k}'], out[f'n_valid_{k}'] = np.float64(s), rot, t, np.int32(n_valid)
         print(f'case {k}: {h}x{w} n_valid {n_valid} |grad_noc| {np.abs(g_noc).max():.3e} |grad_depth| {np.abs(g_depth).max():.3e}')
+    # RANSAC path: gradient through the refit on the winner's inliers (winner and inlier set are locally
+    # constant, so the finite differences see the same piecewise-smooth function the backward kernel differentiates)
+    k = len(cases)
+    noc, depth, mask, xy0 = make_case(rng, 14, 16, 64, 90, 0.85)
+    valid = (mask != 0) & (depth > 0)
+    bad = valid & (rng.uniform(size=depth.shape) < 0.15)
+    depth[bad] += rng.uniform(8.0, 20.0, size=int(bad.sum())).astype(np.float32)     # gross outliers, beyond PassT
+    n_valid = int(valid.sum())
+    sample_idx = rng.integers(0, n_valid, size=(12, 10)).astype(np.int32)
+    g_s, g_r, g_t = rng.normal(), rng.normal(size=(3, 3)), rng.normal(size=3)
+    g_noc, g_depth, (s, rot, t), n_valid2 = finite_differences(pu, pe, noc, depth, mask, xy0, g_s, g_r, g_t, sample_idx)
+    assert n_valid2 == n_valid
+    out[f'noc_{k}'] = np.ascontiguousarray(np.transpose(noc, (2, 0, 1)))
+    out[f'depth_{k}'], out[f'mask_{k}'], out[f'xy0_{k}'] = depth, mask, xy0
+    out[f'g_s_{k}'], out[f'g_R_{k}'], out[f'g_t_{k}'] = np.float64(g_s), g_r, g_t
+    out[f'grad_noc_{k}'] = np.ascontiguousarray(np.transpose(g_noc, (2, 0, 1)))
+    out[f'grad_depth_{k}'] = g_depth
+    out[f's_{k}'], out[f'R_{k}'], out[f't_{k}'], out[f'n_valid_{k}'] = np.float64(s), rot, t, np.int32(n_valid)
+    out[f'sample_idx_{k}'] = sample_idx
+    n_zero = int(((np.abs(g_noc).sum(-1) == 0) & valid).sum())
+    print(f'case {k} (RANSAC): n_valid {n_valid}, {n_zero} valid pixels with zero gradient (outliers), '
+          f'|grad_noc| {np.abs(g_noc).max():.3e}')
+    out['ransac_case'] = np.int32(k)
     out['n_cases'] = np.int32(len(cases))
     out['step'] = np.float64(STEP)
     os.makedirs(GOLD, exist_ok=True)

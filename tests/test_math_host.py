@@ -204,3 +204,24 @@ def test_gradients_match_reference_finite_differences(lib, golden_dir):
             got_z = got_y[:, 0] * rx - got_y[:, 1] * ry - got_y[:, 2]    # y = (rx z, -ry z, -z), pose_estimation.py:34-41
             assert np.abs(got_x - want_x).max() <= 2e-6 * np.abs(want_x).max(), (name, k)
             assert np.abs(got_z - want_z).max() <= 2e-6 * np.abs(want_z).max(), (name, k)
+
+
+def test_ransac_gradients_match_reference_finite_differences(golden_dir):
+    """Same pin for the RANSAC path: finite differences of the real estimateSimilarityTransform (replayed
+    indices) vs the autograd restatement weighted by the oracle's inlier set (winner and inliers locally constant)."""
+    g = np.load(os.path.join(golden_dir, 'grad_fd.npz'))
+    k = int(g['ransac_case'])
+    noc_pts, depth_pts, want_x, want_z, rx, ry = _fd_case(g, k)
+    o = po.similarity_transform(noc_pts, depth_pts, g[f'sample_idx_{k}'])
+    assert o['ok'] and 0 < len(o['inlier_idx']) < noc_pts.shape[0]
+    wts = np.zeros(noc_pts.shape[0])
+    wts[o['inlier_idx']] = 1.0
+    gx, gy, (s, R, t) = grad_oracle.fit_gradients(torch.from_numpy(noc_pts), torch.from_numpy(depth_pts),
+                                                  torch.from_numpy(wts), float(g[f'g_s_{k}']),
+                                                  torch.from_numpy(g[f'g_R_{k}']), torch.from_numpy(g[f'g_t_{k}']))
+    np.testing.assert_allclose(float(s), float(g[f's_{k}']), rtol=1e-12)
+    got_x, got_y = gx.numpy(), gy.numpy()
+    got_z = got_y[:, 0] * rx - got_y[:, 1] * ry - got_y[:, 2]
+    assert np.abs(got_x - want_x).max() <= 2e-6 * np.abs(want_x).max()
+    assert np.abs(got_z - want_z).max() <= 2e-6 * np.abs(want_z).max()
+    assert np.all(want_x[wts == 0] == 0.0)                           # outliers of the winner: exactly no gradient
