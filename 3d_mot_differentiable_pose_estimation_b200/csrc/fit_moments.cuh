@@ -271,9 +271,12 @@ __global__ void __launch_bounds__(512, 1) fit_moments_kernel(const FwdParams p) 
         const float n1[4] = {b4.x, b4.y, b4.z, b4.w};
         const float n2[4] = {c4.x, c4.y, c4.z, c4.w};
         if (row_fast && g.simple) {
-          const double nry = -ryr[row];
-          const double2 rxa = *reinterpret_cast<const double2*>(rxc + col);
-          const double2 rxb = *reinterpret_cast<const double2*>(rxc + col + 2);
+          // lanes past the end of the object (last, partial chunk) carry zeros: keep their table reads
+          // inside the tables (with a narrow crop `row` would run far past H, out of the CTA's shared memory)
+          const int trow = px0 < P ? row : 0, tcol = px0 < P ? col : 0;
+          const double nry = -ryr[trow];
+          const double2 rxa = *reinterpret_cast<const double2*>(rxc + tcol);
+          const double2 rxb = *reinterpret_cast<const double2*>(rxc + tcol + 2);
           const double rx[4] = {rxa.x, rxa.y, rxb.x, rxb.y};
 #pragma unroll
           for (int j = 0; j < 4; ++j) {                       // branch-free: invalid pixels contribute zeros

@@ -127,6 +127,39 @@ def test_ransac_fit_vs_oracle(pf, h, w, b, n_hyp, seed):
     print('ransac', (h, w, n_hyp), worst, 'min margin', min(margins))
 
 
+def test_shape_sweep_vs_oracle(pf):
+    """Every loader / pass variant is picked from the crop shape (W % 4, P % 4, P % 16, P % 128, pointer
+    alignment): sweep small shapes through the plain fit, the RANSAC fit and the backward pass."""
+    shapes = [(1, 1), (1, 4), (2, 2), (3, 5), (4, 4), (4, 8), (5, 12), (8, 8), (7, 16), (12, 16), (16, 12), (10, 20),
+              (16, 16), (17, 16), (24, 20), (20, 28), (31, 32), (32, 33), (40, 36), (48, 40), (50, 50), (33, 64),
+              (64, 40), (72, 56), (96, 100)]
+    for k, (h, w) in enumerate(shapes):
+        b, n_hyp = 3, 6
+        d = pf.synth.make_objects(b, h, w, seed=900 + k, n_hyp=n_hyp, align_x0=1 if w % 4 else 4, border=0,
+                                  mask_fill=0.9, zero_depth_frac=0.0)
+        t = _cuda(d)
+        raw = pf.pose_fit_raw(t['noc'], t['depth'], t['mask'], t['bbox_xy0'])
+        ora = po.batch_pose(d['noc'].numpy(), d['depth'].numpy(), d['mask'].numpy(), d['bbox_xy0'].numpy())
+        # tiny clouds are ill-conditioned (a 1-3 point covariance is singular): statuses and counts always,
+        # poses only where the fit is determined
+        if h * w >= 16:
+            check_against_oracle(raw, ora, ransac=False)
+        else:
+            assert raw.status.cpu().tolist() == [o['status'] for o in ora]
+            assert raw.n_valid.cpu().tolist() == [o['n_valid'] for o in ora]
+        if h * w >= 64:
+            rr = pf.pose_fit_raw(t['noc'], t['depth'], t['mask'], t['bbox_xy0'], sample_idx=t['sample_idx'])
+            orr = po.batch_pose(d['noc'].numpy(), d['depth'].numpy(), d['mask'].numpy(), d['bbox_xy0'].numpy(),
+                                sample_idx=d['sample_idx'].numpy())
+            check_against_oracle(rr, orr, ransac=True)
+        noc = t['noc'].clone().requires_grad_(True)
+        out = pf.pose_fit(noc, t['depth'], t['mask'], t['bbox_xy0'],
+                          sample_idx=t['sample_idx'] if h * w >= 64 else None)
+        (out[0].sum() + out[1].sum() + out[2].sum()).backward()
+        torch.cuda.synchronize()
+        assert torch.isfinite(noc.grad).all(), (h, w)
+
+
 def test_ransac_sparse_masks_vs_oracle(pf):
     """The fast path's select list (every even-ranked valid pixel + next-set-bit for the odd ranks)
     against the oracle on masks with long empty runs, odd / tiny counts and a 112x112 crop (1 CTA/SM)."""

@@ -1,7 +1,7 @@
 #!/bin/bash
 # tests + bench summary in one gpurun call
-timeout 1200 python -m pytest tests -m gpu -q --timeout 600 > gpurun_out/gpu_tests.log 2>&1; echo "pytest exit $?"; tail -4 gpurun_out/gpu_tests.log
-timeout 900 python bench.py --steps 5 --warmup 3 --no-cpu "$@" > gpurun_out/bench.log 2> gpurun_out/bench.err; echo "bench exit $?"; tail -5 gpurun_out/bench.err
+timeout 300 python -m pytest tests -m gpu -q --timeout 120 > gpurun_out/gpu_tests.log 2>&1; echo "pytest exit $?"; tail -4 gpurun_out/gpu_tests.log
+timeout 400 python bench.py --steps 5 --warmup 3 --no-cpu "$@" > gpurun_out/bench.log 2> gpurun_out/bench.err; echo "bench exit $?"; tail -5 gpurun_out/bench.err
 python - <<'PY'
 import json
 d=json.loads(open("gpurun_out/bench.log").read().strip().splitlines()[-1])
