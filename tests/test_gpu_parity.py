@@ -160,6 +160,83 @@ def test_shape_sweep_vs_oracle(pf):
         assert torch.isfinite(noc.grad).all(), (h, w)
 
 
+def test_ransac_parameter_sweep_vs_oracle(pf):
+    """Hypothesis counts around the CTA size (one hypothesis per thread up to 128, shared-memory transforms
+    beyond), sample sizes other than the reference's 10, and inputs that are unaligned views into larger
+    buffers (the 16-byte rules of the bulk / vector loaders must fall back, not fault)."""
+    for k, (n_hyp, n_samp) in enumerate([(1, 10), (7, 3), (127, 10), (128, 4), (129, 10), (200, 16), (300, 10)]):
+        b, h, w = 4, 32, 32
+        d = pf.synth.make_objects(b, h, w, seed=700 + k, n_hyp=n_hyp, n_samp=n_samp)
+        t = _cuda(d)
+        raw = pf.pose_fit_raw(t['noc'], t['depth'], t['mask'], t['bbox_xy0'], sample_idx=t['sample_idx'])
+        ora = po.batch_pose(d['noc'].numpy(), d['depth'].numpy(), d['mask'].numpy(), d['bbox_xy0'].numpy(),
+                            sample_idx=d['sample_idx'].numpy())
+        check_against_oracle(raw, ora, ransac=True)
+    # unaligned views: every input starts 4 (float) / 1 (byte) elements into its buffer
+    for (h, w) in [(32, 32), (20, 28), (15, 17)]:
+        b, n_hyp = 3, 16
+        d = pf.synth.make_objects(b, h, w, seed=750 + h, n_hyp=n_hyp, align_x0=1 if w % 4 else 4)
+
+        def off(x, n):
+            buf = torch.zeros(x.numel() + n, dtype=x.dtype, device='cuda')
+            buf[n:] = x.reshape(-1).cuda()
+            return buf[n:].view(x.shape)
+        noc, depth, mask = off(d['noc'], 1), off(d['depth'], 3), off(d['mask'], 1)
+        assert noc.data_ptr() % 16 != 0 and mask.data_ptr() % 4 != 0
+        ora_p = po.batch_pose(d['noc'].numpy(), d['depth'].numpy(), d['mask'].numpy(), d['bbox_xy0'].numpy())
+        ora_r = po.batch_pose(d['noc'].numpy(), d['depth'].numpy(), d['mask'].numpy(), d['bbox_xy0'].numpy(),
+                              sample_idx=d['sample_idx'].numpy())
+        xy0, idx = d['bbox_xy0'].cuda(), d['sample_idx'].cuda()
+        check_against_oracle(pf.pose_fit_raw(noc, depth, mask, xy0), ora_p, ransac=False)
+        check_against_oracle(pf.pose_fit_raw(noc, depth, mask, xy0, sample_idx=idx), ora_r, ransac=True)
+        nocg = noc.clone().requires_grad_(True)          # clone() realigns; the backward kernel gets the view below
+        out = pf.pose_fit(nocg, depth, mask, xy0)
+        (out[0].sum() + out[1].sum() + out[2].sum()).backward()
+        g_aligned = nocg.grad.clone()
+        raw = pf.pose_fit_raw(noc, depth, mask, xy0)
+        gs = torch.ones(b, device='cuda')
+        g2 = pf.pose_fit_backward_raw(noc, depth, mask, None, xy0, pf.default_kinv('cuda'), raw.ctx, raw.status,
+                                      gs, torch.ones(b, 9, device='cuda'), torch.ones(b, 3, device='cuda'))
+        torch.cuda.synchronize()
+        g2n = g2[0] if isinstance(g2, (tuple, list)) else g2
+        assert float((g2n - g_aligned).abs().max()) <= 1e-6 * float(g_aligned.abs().max())
+
+
+def test_points_mode_size_sweep(pf):
+    """estimateSimilarityUmeyama / estimateSimilarityTransform on explicit point sets of awkward sizes,
+    including the largest staged size and the first one that runs in global-memory mode."""
+    rng = np.random.default_rng(321)
+    for n in (1, 2, 3, 5, 10, 33, 127, 128, 129, 1000, 4600, 4800):
+        b = 2
+        src = rng.uniform(-0.5, 0.5, size=(b, n, 3))
+        dst = np.empty_like(src)
+        for i in range(b):
+            rot = np.linalg.qr(rng.normal(size=(3, 3)))[0]
+            dst[i] = 1.4 * src[i] @ rot.T + np.array([0.2, -0.1, -3.2]) + rng.normal(scale=0.01, size=(n, 3))
+            bad = rng.uniform(size=n) < 0.1
+            dst[i, bad, 2] -= rng.uniform(25, 40, size=int(bad.sum()))
+        s_t = torch.from_numpy(np.ascontiguousarray(src.transpose(0, 2, 1))).cuda()
+        d_t = torch.from_numpy(np.ascontiguousarray(dst.transpose(0, 2, 1))).cuda()
+        plain = pf.points_fit_raw(s_t, d_t, None)
+        pp = plain.pose.cpu().numpy()
+        for i in range(b):
+            scales, rot_t, trans, _ = po.umeyama_fit(src[i], dst[i])
+            if n >= 5:
+                assert rot_err_deg(pp[i, 1:10].reshape(3, 3), rot_t.T) < 1e-6, n
+                np.testing.assert_allclose(pp[i, 0], scales[0], rtol=1e-8)
+            assert int(plain.status[i]) == 0 and int(plain.n_valid[i]) == n
+        if n >= 10:
+            idx = rng.integers(0, n, size=(b, 24, 10)).astype(np.int32)
+            rans = pf.points_fit_raw(s_t, d_t, None, sample_idx=torch.from_numpy(idx).cuda())
+            for i in range(b):
+                o = po.similarity_transform(src[i], dst[i], idx[i])
+                assert int(rans.status[i]) == (0 if o['ok'] else 2), n
+                if o['ok']:
+                    want = np.zeros(n, dtype=np.uint8)
+                    want[o['inlier_idx']] = 1
+                    np.testing.assert_array_equal(rans.inlier_mask[i].cpu().numpy(), want, err_msg=str(n))
+
+
 def test_ransac_sparse_masks_vs_oracle(pf):
     """The fast path's select list (every even-ranked valid pixel + next-set-bit for the odd ranks)
     against the oracle on masks with long empty runs, odd / tiny counts and a 112x112 crop (1 CTA/SM)."""
