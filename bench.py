@@ -229,6 +229,12 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------------------
+def workload_name(n_obj, size):
+    """config.workload, shared by both arms."""
+    return (f'config-5 shard: {n_obj} objects/GPU ({SEQ_PER_GPU} sequences x {FRAMES_PER_SEQ} frames x {OBJ_PER_FRAME} '
+            f'objects) x {size}x{size} NOC+depth+mask crops, plain Umeyama fit fwd + bwd, sharded by sequence')
+
+
 def peaks():
     path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(path):
@@ -507,9 +513,7 @@ def run_ours(args):
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-            'config': {'workload': f'config-5 shard: {n_obj} objects/GPU ({SEQ_PER_GPU} sequences x {FRAMES_PER_SEQ} '
-                                   f'frames x {OBJ_PER_FRAME} objects) x {size}x{size} NOC+depth+mask crops, plain '
-                                   f'Umeyama fit fwd + bwd, sharded by sequence',
+            'config': {'workload': workload_name(n_obj, size),
                        'objects_per_gpu': n_obj, 'crop': [size, size],
                        'l2': 'inputs per step (%.1f GB) exceed the 126 MB L2; no flush needed' % (n_obj * 17 * P / 1e9),
                        'collective': ('all_gather of 128-B pose records per step, queued beside the backward pass'
@@ -542,8 +546,9 @@ def run_reference(args):
     line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': n / value * 1e3, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-            'config': {'workload': f'config-5 shard objects, {args.size}x{args.size} crops, plain Umeyama fit fwd + bwd',
-                       'objects_per_step': n},
+            'config': {'workload': workload_name(args.objects, args.size), 'objects_per_gpu': args.objects,
+                       'crop': [args.size, args.size],
+                       'sample': f'{n} objects of that workload per step (CPU arm: bounded sample, same generator)'},
             'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': used, 'kind': 'port', 'sample': what},
             'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}

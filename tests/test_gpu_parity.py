@@ -352,6 +352,14 @@ def test_edge_cases(pf):
     assert p3[0] == 1.0 and np.array_equal(p3[1:10].reshape(3, 3), np.identity(3))
     rr = pf.pose_fit_raw(t['noc'], t['depth'], t['mask'], t['bbox_xy0'], sample_idx=t['sample_idx'])
     assert rr.status.cpu().tolist()[:2] == [1, 1]
+    # objects the fit rejects (empty, NaN, low inlier ratio) contribute exactly zero gradient, the others finite ones
+    noc = t['noc'].clone().requires_grad_(True)
+    dep = t['depth'].clone().requires_grad_(True)
+    out = pf.pose_fit(noc, dep, t['mask'], t['bbox_xy0'])
+    (out[0].sum() + out[1].sum() + out[2].sum()).backward()
+    for i in (0, 1, 2):
+        assert float(noc.grad[i].abs().max()) == 0.0 and float(dep.grad[i].abs().max()) == 0.0
+    assert torch.isfinite(noc.grad).all() and float(noc.grad[4].abs().max()) > 0.0
     # zero hypotheses: nothing accepted, BestInlierRatio stays 0 -> 4xNone (pose_utils.py:68-70,105)
     z = pf.pose_fit_raw(t['noc'][4:], t['depth'][4:], t['mask'][4:], t['bbox_xy0'][4:],
                         sample_idx=torch.zeros(2, 0, 10, dtype=torch.int32, device='cuda'))
