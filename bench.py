@@ -291,19 +291,23 @@ def run_ours(args):
     g_t = torch.randn(n_obj, 3, device=dev, generator=gen)
     kinv = pf.default_kinv(dev)
 
+    gather_async = os.environ.get('POSEFIT_BENCH_GATHER', 'sync') == 'async'
+
     def step():
         e0, e1, e2 = ev(), ev(), ev()
         e0.record()
         raw = pf.pose_fit_raw(d['noc'], d['depth'], d['mask'], d['bbox_xy0'], kinv)
         e1.record()
         work = None
-        if world > 1:                                            # the one collective: gather of the pose records,
+        if world > 1 and gather_async:                           # the one collective: gather of the pose records,
             _, work = pf.shard.gather_poses(raw.pose, async_op=True)   # queued behind the fit, beside the backward pass
         pf.pose_fit_backward_raw(d['noc'], d['depth'], d['mask'], None, d['bbox_xy0'], kinv, raw.ctx, raw.status,
                                  g_s, g_R, g_t)
         e2.record()
         if work is not None:
             work.wait()
+        elif world > 1:
+            pf.shard.gather_poses(raw.pose)                      # after the backward pass, on the same stream
         return [('fit_moments_kernel', e0, e1), ('fit_backward_kernel', e1, e2)]
 
     for _ in range(args.warmup):
@@ -516,7 +520,8 @@ def run_ours(args):
             'config': {'workload': workload_name(n_obj, size),
                        'objects_per_gpu': n_obj, 'crop': [size, size],
                        'l2': 'inputs per step (%.1f GB) exceed the 126 MB L2; no flush needed' % (n_obj * 17 * P / 1e9),
-                       'collective': ('all_gather of 128-B pose records per step, queued beside the backward pass'
+                       'collective': (('all_gather of 128-B pose records per step, ' +
+                                       ('queued beside the backward pass' if gather_async else 'after the backward pass'))
                                       if world > 1 else 'none'),
                        'host_numa_node': numa_node},
             'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': int(launches),

@@ -1,4 +1,5 @@
-python bench.py > gpurun_out/s17_ours.json 2> gpurun_out/s17_ours.err; echo "ours rc $?"
-python bench.py --impl reference > gpurun_out/s17_ref.json 2> gpurun_out/s17_ref.err; echo "ref rc $?"
-ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"fit_|pose_" -c 400 --csv --log-file gpurun_out/s17_launches.csv python bench.py --steps 5 --warmup 3 --no-cpu > gpurun_out/s17_ncu.log 2>&1; echo "ncu rc $?"
-python tools/prof_case.py c3 1 > /dev/null && ncu --set full --import-source on --clock-control none -k regex:fit_ransac -c 1 -o gpurun_out/s17_ransac_c3 python tools/prof_case.py c3 1 > gpurun_out/s17_r.log 2>&1; echo "ncu2 rc $?"
+for mode in sync async sync async; do
+POSEFIT_BENCH_GATHER=$mode timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 2 --steps 50 --warmup 5 --no-cpu --no-extra --e2e-objects 256 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('$mode', 'ms/step %.3f'%d['ms_per_step'], 'value %.3e'%d['value'], d['clocks']['sm_mhz'])"
+done
