@@ -320,6 +320,39 @@ def test_tma_and_fallback_loaders_agree(pf, monkeypatch):
     assert torch.equal(ar.inlier_mask, br.inlier_mask)
 
 
+def test_launch_variants_agree(pf, monkeypatch):
+    """Every launch-time knob of the library (CTA size of the RANSAC kernel, ring depth / vector loads / PDL /
+    warm-up pass of the plain path) selects a different kernel instantiation or schedule, never a different
+    result: masks, winners and statuses identical, poses to rounding."""
+    d = pf.synth.make_objects(48, 64, 64, seed=23, n_hyp=64)
+    t = _cuda(d)
+    g = (torch.randn(48, device='cuda'), torch.randn(48, 9, device='cuda'), torch.randn(48, 3, device='cuda'))
+
+    def run():
+        plain = pf.pose_fit_raw(t['noc'], t['depth'], t['mask'], t['bbox_xy0'])
+        rans = pf.pose_fit_raw(t['noc'], t['depth'], t['mask'], t['bbox_xy0'], sample_idx=t['sample_idx'])
+        gn, _ = pf.pose_fit_backward_raw(t['noc'], t['depth'], t['mask'], None, t['bbox_xy0'], None, plain.ctx,
+                                         plain.status, *g)
+        torch.cuda.synchronize()
+        return plain, rans, gn
+    base = run()
+    variants = [{'POSEFIT_RANSAC_THREADS': '256'}, {'POSEFIT_RANSAC_THREADS': '256', 'POSEFIT_RANSAC_MINB': '3'},
+                {'POSEFIT_RANSAC_CTAS_PER_SM': '1'}, {'POSEFIT_NO_VEC': '1'}, {'POSEFIT_DEPTH': '2'},
+                {'POSEFIT_DEPTH': '4'}, {'POSEFIT_NO_PDL': '1'}, {'POSEFIT_PREWARM': '0'}, {'POSEFIT_PREWARM': '1'},
+                {'POSEFIT_EARLY_DEP': '0'}, {'POSEFIT_EARLY_DEP': '15'}, {'POSEFIT_CTAS_PER_SM': '2'}]
+    for env in variants:
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        plain, rans, gn = run()
+        for k in env:
+            monkeypatch.delenv(k)
+        assert torch.equal(plain.status, base[0].status) and torch.equal(rans.status, base[1].status), env
+        assert torch.equal(rans.inlier_mask, base[1].inlier_mask) and torch.equal(rans.winner, base[1].winner), env
+        assert float((plain.pose[:, :13] - base[0].pose[:, :13]).abs().max()) < 1e-10, env
+        assert float((rans.pose[:, :13] - base[1].pose[:, :13]).abs().max()) < 1e-10, env
+        assert float((gn - base[2]).abs().max()) <= 1e-5 * float(base[2].abs().max()), env
+
+
 def test_ransac_fast_and_generic_passes_agree(pf, monkeypatch):
     d = pf.synth.make_objects(64, 64, 64, seed=22, n_hyp=128)
     t = _cuda(d)
