@@ -266,12 +266,14 @@ def test_gt_box_clip_mask(pf):
         np.testing.assert_array_equal(got[i].cpu().numpy(), want_masks[i])
 
 
-def test_statistical_outlier_mask(pf):
-    """posefit_sor_mask vs the oracle restatement of Open3D's remove_statistical_outlier (unpinned)."""
-    b, h, w = 6, 48, 56
-    d = pf.synth.make_objects(b, h, w, seed=95)
+@pytest.mark.parametrize('h,w', [(48, 56), (13, 17), (46, 45), (64, 64), (90, 100)])
+def test_statistical_outlier_mask(pf, h, w):
+    """posefit_sor_mask vs the oracle restatement of Open3D's remove_statistical_outlier (unpinned).
+    Shapes: below / at / across the kernel's 2048-point tile and its 256-thread rounds, odd widths."""
+    b = 6
+    d = pf.synth.make_objects(b, h, w, seed=95, align_x0=1 if w % 4 else 4)
     d['mask'][4] = 0
-    d['mask'][4, 10:14, 10:20] = 1                        # 40 points: below the 100-point rule -> untouched
+    d['mask'][4, 5:9, 4:14] = 1                           # 40 points: below the 100-point rule -> untouched
     t = {k: d[k].cuda() for k in ('noc', 'depth', 'mask', 'bbox_xy0')}
     m1 = pf.statistical_outlier_mask(None, t['depth'], t['mask'], t['bbox_xy0'], source='depth')
     m2 = pf.statistical_outlier_mask(t['noc'], t['depth'], m1, t['bbox_xy0'], source='noc')
@@ -293,4 +295,5 @@ def test_statistical_outlier_mask(pf):
         np.testing.assert_array_equal(m2[i].cpu().numpy(), want2)
     n4 = int(((d['mask'][4] != 0) & (d['depth'][4] > 0)).sum())
     assert 30 <= n4 <= 40 and int(m1[4].sum()) == n4     # fewer than 100 points: left untouched (:311)
-    assert int(m1[0].sum()) < int(d['n_valid'][0])        # the gross outliers are gone
+    if h * w > 1000:
+        assert int(m1[0].sum()) < int(d['n_valid'][0])    # the gross outliers are gone
