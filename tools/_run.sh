@@ -1,5 +1,7 @@
-for mode in sync async sync async; do
-POSEFIT_BENCH_GATHER=$mode timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 2 --steps 50 --warmup 5 --no-cpu --no-extra --e2e-objects 256 2>/dev/null | python -c "
+for cfg in "12 4" "14 4" "14 6" "13 6" "12 6" "15 4" "12 4"; do
+set -- $cfg
+POSEFIT_SMALL_WARPS=$1 POSEFIT_DEPTH=$2 timeout 200 python bench.py --steps 3 --warmup 3 --no-cpu 2>/dev/null | python -c "
 import json,sys
-d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('$mode', 'ms/step %.3f'%d['ms_per_step'], 'value %.3e'%d['value'], d['clocks']['sm_mhz'])"
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); c=d['configs']
+print('warps $1 depth $2:', ' '.join('%s %.4f' % (k.split()[0], v['ms']) for k,v in c.items()))"
 done
