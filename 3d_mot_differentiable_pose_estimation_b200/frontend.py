@@ -89,3 +89,61 @@ class ResampleNoc(torch.autograd.Function):
 
 def resample_noc(noc_head, roi_hw, height: int, width: int):
     return ResampleNoc.apply(noc_head, roi_hw, height, width)
+
+
+class BatchedPoses(NamedTuple):
+    """Everything run_pose returns per instance (pose_estimation.py:401-412), for the whole batch, on the GPU."""
+    global_rot: torch.Tensor     # [B,3,3] f64, scale embedded (:404-406)
+    global_trans: torch.Tensor   # [B,3]
+    global_scale: torch.Tensor   # [B]
+    euler: torch.Tensor          # [B,3] XYZ Euler angles of the unscaled rotation (postprocess.py:158-160)
+    world_box: torch.Tensor      # [B,8,3] sort_bbox-ordered world box of the depth points (:373-380)
+    status: torch.Tensor         # [B] i32: 0 ok; 1 / 2 = the cases run_pose answers with 6 x None; 3 = NaN input
+    raw: object                  # PoseFitRaw of the fit (camera-space s, R, t, inlier mask, context for backward)
+    noc: torch.Tensor            # [B,3,H,W] resampled NOC crops (differentiable w.r.t. the head output)
+    crops: Crops
+    mask: torch.Tensor           # [B,H,W] u8 correspondences that reached the fit (after the pre-filters)
+
+
+def run_pose_batched(pred_nocs, depth_frames, inst_masks, boxes_xyxy, frame_of: Optional[torch.Tensor] = None,
+                     campose=None, kinv=None, gt_boxes=None, ransac: bool = True, n_iterations: int = 100,
+                     n_samples: int = 10, apply_statistical_filter: bool = True, sample_idx=None,
+                     height: Optional[int] = None, width: Optional[int] = None) -> BatchedPoses:
+    """The per-instance loop of `postprocess_dets` (Detection/tracker/postprocess.py:131-165) -- roi_align of
+    the NOC head output, depth / mask slicing, run_pose -- for ALL instances of a batch of frames at once.
+
+    pred_nocs [B,3,Hh,Wh] head outputs; depth_frames [F,FH,FW]; inst_masks [B,FH,FW]; boxes_xyxy [B,4];
+    frame_of [B] frame index of each instance (None: one frame); campose [4,4] / [F,4,4] camera-to-world
+    (None keeps camera space, as run_pose_office); gt_boxes [B,8,3] enables the clean_depth clip (:293-299).
+    RANSAC indices are drawn from the global `np.random` stream exactly as the per-instance drop-in does
+    (instance after instance, `randint(N_i, size=(n_iterations, n_samples))`, nothing for an empty instance)
+    unless `sample_idx` [B,n_hyp,n_samp] is given; the only host round trip is the B correspondence counts
+    that `randint` needs.  Instances are padded to one H x W (default: the largest box, width rounded up to 4)."""
+    import numpy as np
+    from .function import (pose_fit_raw, pose_epilogue, clip_mask_to_box, statistical_outlier_mask)
+    boxes = torch.as_tensor(boxes_xyxy)
+    if height is None or width is None:
+        bh = int((boxes[:, 3] - boxes[:, 1]).max()) if boxes.numel() else 1
+        bw = int((boxes[:, 2] - boxes[:, 0]).max()) if boxes.numel() else 1
+        height = height or max(bh, 1)
+        width = width or max((bw + 3) // 4 * 4, 4)
+    crops = gather_crops(depth_frames, inst_masks, boxes, frame_of, height, width)
+    noc = resample_noc(pred_nocs, crops.roi_hw, height, width)
+    mask = crops.mask
+    cam_index = frame_of if (campose is not None and torch.as_tensor(campose).dim() == 3) else None
+    if gt_boxes is not None and campose is not None:
+        mask, _ = clip_mask_to_box(crops.depth, mask, crops.bbox_xy0, gt_boxes, campose, kinv, cam_index=cam_index)
+    if apply_statistical_filter:
+        mask = statistical_outlier_mask(None, crops.depth, mask, crops.bbox_xy0, kinv, source='depth')
+        mask = statistical_outlier_mask(noc.detach(), crops.depth, mask, crops.bbox_xy0, kinv, source='noc')
+    if ransac and sample_idx is None:
+        counts = ((mask != 0) & (crops.depth > 0)).flatten(1).sum(1).cpu().numpy()     # the one host round trip
+        idx = np.zeros((len(counts), n_iterations, n_samples), dtype=np.int32)
+        for i, n in enumerate(counts):
+            if n > 0:
+                idx[i] = np.random.randint(int(n), size=(n_iterations, n_samples))     # pose_utils.py:73
+        sample_idx = torch.from_numpy(idx)
+    raw = pose_fit_raw(noc.detach(), crops.depth, mask, crops.bbox_xy0, kinv, sample_idx=sample_idx if ransac else None)
+    epi = pose_epilogue(raw, crops.depth, mask, crops.bbox_xy0, kinv, campose=campose, cam_index=cam_index)
+    return BatchedPoses(epi.global_rot, epi.global_trans, epi.global_scale, epi.euler, epi.world_box, raw.status, raw,
+                        noc, crops, mask)

@@ -103,3 +103,57 @@ def test_batched_pipeline_equals_per_instance_reference_flow(pf):
         assert ang <= 1e-3
         np.testing.assert_allclose(pose[0], o['s'], rtol=1e-5)
         np.testing.assert_allclose(pose[10:13], o['t'], rtol=1e-5)
+
+
+def test_run_pose_batched_equals_per_instance_drop_in(pf):
+    """run_pose_batched (one call for all instances of two frames) vs the per-instance drop-in
+    pose_estimation.run_pose fed with the reference-style roi_align patches, same np.random stream:
+    global rotation / translation / scale and the world boxes agree; an empty instance is status 1."""
+    rng = np.random.default_rng(8)
+    gen = torch.Generator().manual_seed(8)
+    FH, FW = 240, 320
+    boxes = np.array([[40, 30, 100, 94], [150, 60, 222, 110], [10, 150, 60, 214], [200, 120, 264, 180], [90, 90, 131, 123],
+                      [5, 5, 165, 125]], dtype=np.int32)                      # the last box: 120 x 160 (global-memory RANSAC mode)
+    b = boxes.shape[0]
+    frame_of = np.array([0, 0, 1, 1, 0, 1], dtype=np.int32)
+    head = torch.rand(b, 3, 28, 28, generator=gen)
+    # a consistent scene per instance: depth generated from the NOC patch through a known similarity
+    depth = np.zeros((2, FH, FW), dtype=np.float32)
+    masks = np.zeros((b, FH, FW), dtype=bool)
+    k = po.motfront_intrinsics()
+    for i in range(b):
+        x0, y0, x1, y1 = boxes[i]
+        h, w = y1 - y0, x1 - x0
+        patch = _reference_patch(head[i], h, w).permute(1, 2, 0).numpy().astype(np.float64)
+        rot = np.linalg.qr(rng.normal(size=(3, 3)))[0]
+        rot *= np.sign(np.linalg.det(rot))
+        pts = 1.5 * (patch.reshape(-1, 3) - 0.5) @ rot.T + np.array([0.0, 0.0, -3.5])
+        z = (-pts[:, 2]).reshape(h, w) + rng.normal(scale=0.01, size=(h, w))
+        m = rng.uniform(size=(h, w)) < 0.8
+        free = depth[frame_of[i], y0:y1, x0:x1] == 0
+        depth[frame_of[i], y0:y1, x0:x1] = np.where(free, z, depth[frame_of[i], y0:y1, x0:x1]).astype(np.float32)
+        masks[i, y0:y1, x0:x1] = m & free
+    masks[4] = False                                                           # an empty instance -> 6 x None / status 1
+    campose = np.tile(np.identity(4), (2, 1, 1))
+    for f in range(2):
+        campose[f, :3, :3] = np.linalg.qr(rng.normal(size=(3, 3)))[0]
+        campose[f, :3, 3] = rng.normal(size=3)
+    np.random.seed(1234)
+    out = pf.run_pose_batched(head.cuda(), torch.from_numpy(depth).cuda(), torch.from_numpy(masks).cuda(),
+                              torch.from_numpy(boxes).cuda(), torch.from_numpy(frame_of).cuda(),
+                              campose=torch.from_numpy(campose))
+    np.random.seed(1234)
+    for i in range(b):
+        x0, y0, x1, y1 = boxes[i]
+        patch = _reference_patch(head[i], y1 - y0, x1 - x0).permute(1, 2, 0).contiguous()
+        ref = pf.pose_estimation.run_pose(patch.cuda(), depth[frame_of[i]], campose[frame_of[i]],
+                                          torch.from_numpy(masks[i]).cuda(), tuple(int(v) for v in boxes[i]))
+        if ref[0] is None:
+            assert int(out.status[i]) in (1, 2)
+            continue
+        assert int(out.status[i]) == 0
+        np.testing.assert_allclose(out.global_rot[i].cpu().numpy(), ref[0], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(out.global_trans[i].cpu().numpy(), ref[1], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(float(out.global_scale[i]), ref[2], rtol=1e-5)
+        np.testing.assert_allclose(out.world_box[i].cpu().numpy(), ref[3], rtol=1e-6, atol=1e-6)
+    assert int(out.status[4]) == 1
