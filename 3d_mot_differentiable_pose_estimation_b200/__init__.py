@@ -10,7 +10,7 @@ own modules (same function names and signatures); `synth.py` makes MOTFront-shap
 `shard.py` partitions objects by sequence across GPUs.
 """
 from . import _lib  # noqa: F401
-from .function import (PoseFit, PoseFitRaw, pose_fit, pose_fit_raw, points_fit_raw,  # noqa: F401
+from .function import (PoseFit, PoseFitFull, PoseFitRaw, pose_fit, pose_fit_raw, points_fit_raw,  # noqa: F401
                        pose_fit_backward_raw, default_kinv, pose_epilogue, PoseEpilogue, clip_mask_to_box, statistical_outlier_mask,
                        STATUS_OK, STATUS_EMPTY, STATUS_LOW_INLIER_RATIO, STATUS_NAN)
 from . import synth, shard  # noqa: F401

@@ -99,7 +99,10 @@ class BatchedPoses(NamedTuple):
     euler: torch.Tensor          # [B,3] XYZ Euler angles of the unscaled rotation (postprocess.py:158-160)
     world_box: torch.Tensor      # [B,8,3] sort_bbox-ordered world box of the depth points (:373-380)
     status: torch.Tensor         # [B] i32: 0 ok; 1 / 2 = the cases run_pose answers with 6 x None; 3 = NaN input
-    raw: object                  # PoseFitRaw of the fit (camera-space s, R, t, inlier mask, context for backward)
+    scale: torch.Tensor          # [B]     camera-space fit, connected to autograd when pred_nocs requires grad:
+    rot: torch.Tensor            # [B,3,3] the TRUE rotation (object -> camera is [s R | t], pose_estimation.py:401-403)
+    trans: torch.Tensor          # [B,3]
+    raw: object                  # PoseFitRaw of the fit (float64 records, inlier mask, winners)
     noc: torch.Tensor            # [B,3,H,W] resampled NOC crops (differentiable w.r.t. the head output)
     crops: Crops
     mask: torch.Tensor           # [B,H,W] u8 correspondences that reached the fit (after the pre-filters)
@@ -120,7 +123,7 @@ def run_pose_batched(pred_nocs, depth_frames, inst_masks, boxes_xyxy, frame_of: 
     unless `sample_idx` [B,n_hyp,n_samp] is given; the only host round trip is the B correspondence counts
     that `randint` needs.  Instances are padded to one H x W (default: the largest box, width rounded up to 4)."""
     import numpy as np
-    from .function import (pose_fit_raw, pose_epilogue, clip_mask_to_box, statistical_outlier_mask)
+    from .function import (PoseFitFull, PoseFitRaw, pose_epilogue, clip_mask_to_box, statistical_outlier_mask)
     boxes = torch.as_tensor(boxes_xyxy)
     if height is None or width is None:
         bh = int((boxes[:, 3] - boxes[:, 1]).max()) if boxes.numel() else 1
@@ -143,7 +146,10 @@ def run_pose_batched(pred_nocs, depth_frames, inst_masks, boxes_xyxy, frame_of: 
             if n > 0:
                 idx[i] = np.random.randint(int(n), size=(n_iterations, n_samples))     # pose_utils.py:73
         sample_idx = torch.from_numpy(idx)
-    raw = pose_fit_raw(noc.detach(), crops.depth, mask, crops.bbox_xy0, kinv, sample_idx=sample_idx if ransac else None)
+    # one forward feeds both autograd (the reference detaches here, postprocess.py:151; we do not have to) and the epilogue
+    scale, rot, trans, inl, status, n_valid, pose64, winner = PoseFitFull.apply(
+        noc, crops.depth, mask, crops.bbox_xy0, kinv, sample_idx if ransac else None, 1.0, True)
+    raw = PoseFitRaw(pose64, None, status, n_valid, inl if ransac else None, winner if ransac else None)
     epi = pose_epilogue(raw, crops.depth, mask, crops.bbox_xy0, kinv, campose=campose, cam_index=cam_index)
-    return BatchedPoses(epi.global_rot, epi.global_trans, epi.global_scale, epi.euler, epi.world_box, raw.status, raw,
-                        noc, crops, mask)
+    return BatchedPoses(epi.global_rot, epi.global_trans, epi.global_scale, epi.euler, epi.world_box, status,
+                        scale, rot, trans, raw, noc, crops, mask)

@@ -328,3 +328,34 @@ def pose_fit(noc, depth, mask, bbox_xy0, kinv=None, sample_idx=None, ratio_adapt
              ref_compat: bool = True):
     """Keyword-friendly PoseFit.apply."""
     return PoseFit.apply(noc, depth, mask, bbox_xy0, kinv, sample_idx, ratio_adapt, ref_compat)
+
+
+class PoseFitFull(torch.autograd.Function):
+    """PoseFit that also hands out the float64 pose records and the RANSAC winners (non-differentiable), for
+    callers that feed both autograd (scale, R, t) and the batched epilogue (records): one forward, not two.
+    Returns (scale, R, t, inlier_mask, status, n_valid, pose64 [B,16], winner [B] or empty)."""
+
+    @staticmethod
+    def forward(ctx, noc, depth, mask, bbox_xy0, kinv=None, sample_idx=None, ratio_adapt=1.0, ref_compat=True):
+        raw = pose_fit_raw(noc, depth, mask, bbox_xy0, kinv, sample_idx, ratio_adapt, ref_compat)
+        b = noc.shape[0]
+        inl = raw.inlier_mask
+        ctx.has_inliers = inl is not None
+        ctx.kinv = kinv
+        ctx.depth_grad = bool(depth.requires_grad)
+        ctx.in_dtypes = (noc.dtype, depth.dtype)
+        ctx.save_for_backward(noc, depth, mask, bbox_xy0, raw.ctx, raw.status,
+                              inl if inl is not None else torch.empty(0, device=noc.device))
+        out_dtype = noc.dtype if noc.dtype.is_floating_point else torch.float32
+        scale = raw.pose[:, 0].to(out_dtype)
+        rot = raw.pose[:, 1:10].reshape(b, 3, 3).to(out_dtype)
+        trans = raw.pose[:, 10:13].to(out_dtype)
+        if inl is None:
+            inl = ((mask != 0) & (depth > 0)).to(torch.uint8)
+        winner = raw.winner if raw.winner is not None else torch.empty(0, dtype=torch.int32, device=noc.device)
+        ctx.mark_non_differentiable(inl, raw.status, raw.n_valid, raw.pose, winner)
+        return scale, rot, trans, inl, raw.status, raw.n_valid, raw.pose, winner
+
+    @staticmethod
+    def backward(ctx, g_scale, g_rot, g_trans, *_unused):
+        return PoseFit.backward(ctx, g_scale, g_rot, g_trans)

@@ -157,3 +157,27 @@ def test_run_pose_batched_equals_per_instance_drop_in(pf):
         np.testing.assert_allclose(float(out.global_scale[i]), ref[2], rtol=1e-5)
         np.testing.assert_allclose(out.world_box[i].cpu().numpy(), ref[3], rtol=1e-6, atol=1e-6)
     assert int(out.status[4]) == 1
+
+
+def test_run_pose_batched_is_differentiable_to_the_head_output(pf):
+    """Gradients of a pose loss reach the NOC head output through the fit and the resample -- the end-to-end
+    path the reference cuts at postprocess.py:151 -- and equal the explicit composition resample -> pose_fit."""
+    gen = torch.Generator().manual_seed(9)
+    rng = np.random.default_rng(9)
+    boxes = torch.tensor([[40, 30, 100, 94], [150, 60, 222, 110], [10, 150, 60, 214]], dtype=torch.int32)
+    b = boxes.shape[0]
+    head = torch.rand(b, 3, 28, 28, generator=gen).cuda().requires_grad_(True)
+    depth = torch.from_numpy(rng.uniform(2.0, 5.0, size=(1, 240, 320)).astype(np.float32)).cuda()
+    masks = torch.from_numpy(rng.uniform(size=(b, 240, 320)) < 0.7).cuda()
+    out = pf.run_pose_batched(head, depth, masks, boxes.cuda(), ransac=False, apply_statistical_filter=False)
+    assert out.scale.requires_grad and int((out.status != 0).sum()) == 0
+    w_s, w_r, w_t = torch.randn(b, device='cuda'), torch.randn(b, 3, 3, device='cuda'), torch.randn(b, 3, device='cuda')
+    ((out.scale * w_s).sum() + (out.rot * w_r).sum() + (out.trans * w_t).sum()).backward()
+    g1 = head.grad.clone()
+    head2 = head.detach().clone().requires_grad_(True)
+    noc = pf.resample_noc(head2, out.crops.roi_hw, out.noc.shape[2], out.noc.shape[3])
+    s2, r2, t2, _, _, _ = pf.pose_fit(noc, out.crops.depth, out.crops.mask, out.crops.bbox_xy0)
+    ((s2 * w_s).sum() + (r2 * w_r).sum() + (t2 * w_t).sum()).backward()
+    assert torch.isfinite(g1).all() and float(g1.abs().max()) > 0
+    # (the resample adjoint accumulates with float atomics: equal up to summation order)
+    assert float((g1 - head2.grad).abs().max()) <= 1e-5 * float(g1.abs().max())
