@@ -87,3 +87,49 @@ def bind_host_to_gpu(device_index: int, sysfs: str = '/sys') -> Optional[int]:
         return node
     except (OSError, ValueError, AttributeError, RuntimeError, AssertionError):
         return None
+
+
+class PeerPoseGather:
+    """All-gather of the pose records over NVLink peer memory, moved by the copy engines.
+
+    Every rank owns a [world * n_local, width] buffer in symmetric memory (torch.distributed._symmetric_memory:
+    each buffer is mapped into every peer's address space).  `start(local)` queues, on a side stream and behind
+    the work already on the current stream, one device-to-device copy of this rank's records into its slot of
+    EVERY rank's buffer, then a signal-pad barrier; `wait()` makes the current stream wait for that barrier and
+    returns the gathered tensor.  No SM is occupied by the transfer, so unlike an NCCL all-gather it can run
+    beside an HBM-bound kernel without displacing its CTAs.  The caller must not `start` the next gather while
+    a peer may still be reading the previous result (one step of slack is enough in a training loop).
+    Construction is collective; it raises if symmetric memory is not available (callers fall back to
+    `gather_poses`, the NCCL path)."""
+
+    def __init__(self, n_local: int, width: int = 16, dtype=torch.float64, group=None, timeout_ms: int = 20000):
+        import torch.distributed._symmetric_memory as symm
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        self.n = int(n_local)
+        self.timeout_ms = int(timeout_ms)
+        dev = torch.device('cuda', torch.cuda.current_device())
+        self.buf = symm.empty(self.world * self.n, width, dtype=dtype, device=dev)
+        self.hdl = symm.rendezvous(self.buf, self.group)
+        self.peers = [self.hdl.get_buffer(r, (self.world * self.n, width), dtype) for r in range(self.world)]
+        self.stream = torch.cuda.Stream()
+        self.done = torch.cuda.Event()
+
+    def start(self, local: torch.Tensor) -> None:
+        if tuple(local.shape) != (self.n, self.buf.shape[1]) or local.dtype != self.buf.dtype:
+            raise ValueError('local records do not match the gather buffer')
+        local = local.contiguous()
+        self.stream.wait_stream(torch.cuda.current_stream())
+        lo = self.rank * self.n
+        with torch.cuda.stream(self.stream):
+            local.record_stream(self.stream)
+            for k in range(self.world):
+                r = (self.rank + k) % self.world                 # every rank starts with a different target
+                self.peers[r][lo:lo + self.n].copy_(local, non_blocking=True)
+            self.hdl.barrier(channel=0, timeout_ms=self.timeout_ms)   # all ranks' copies have landed
+            self.done.record(self.stream)
+
+    def wait(self) -> torch.Tensor:
+        torch.cuda.current_stream().wait_event(self.done)
+        return self.buf

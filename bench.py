@@ -291,7 +291,22 @@ def run_ours(args):
     g_t = torch.randn(n_obj, 3, device=dev, generator=gen)
     kinv = pf.default_kinv(dev)
 
-    gather_async = os.environ.get('POSEFIT_BENCH_GATHER', 'sync') == 'async'
+    # The one collective: every step all-gathers the 128-byte pose records.  Default: copies over NVLink peer
+    # memory by the copy engines (shard.PeerPoseGather: no SM is taken from the HBM-bound backward kernel it
+    # runs beside); POSEFIT_BENCH_GATHER=sync|async selects the NCCL all_gather after / beside the backward pass,
+    # which is also the fallback when symmetric memory is not available.
+    gather_mode = os.environ.get('POSEFIT_BENCH_GATHER', 'peer') if world > 1 else 'none'
+    peer = None
+    if gather_mode == 'peer':
+        ok = torch.ones(1, device=dev)
+        try:
+            peer = pf.shard.PeerPoseGather(n_obj)
+        except Exception as e:      # noqa: BLE001  (symmetric memory is optional; NCCL always works)
+            print('bench: peer-memory gather unavailable (%s), using NCCL' % str(e).splitlines()[0], file=sys.stderr)
+            ok.zero_()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if float(ok) == 0.0:
+            peer, gather_mode = None, 'sync'
 
     def step():
         e0, e1, e2 = ev(), ev(), ev()
@@ -299,20 +314,37 @@ def run_ours(args):
         raw = pf.pose_fit_raw(d['noc'], d['depth'], d['mask'], d['bbox_xy0'], kinv)
         e1.record()
         work = None
-        if world > 1 and gather_async:                           # the one collective: gather of the pose records,
-            _, work = pf.shard.gather_poses(raw.pose, async_op=True)   # queued behind the fit, beside the backward pass
+        if gather_mode == 'peer':
+            peer.start(raw.pose)                                 # copy engines, beside the backward pass
+        elif gather_mode == 'async':
+            _, work = pf.shard.gather_poses(raw.pose, async_op=True)
         pf.pose_fit_backward_raw(d['noc'], d['depth'], d['mask'], None, d['bbox_xy0'], kinv, raw.ctx, raw.status,
                                  g_s, g_R, g_t)
         e2.record()
-        if work is not None:
+        if gather_mode == 'peer':
+            peer.wait()
+        elif work is not None:
             work.wait()
-        elif world > 1:
-            pf.shard.gather_poses(raw.pose)                      # after the backward pass, on the same stream
+        elif gather_mode == 'sync':
+            pf.shard.gather_poses(raw.pose)                      # NCCL, after the backward pass, on the same stream
         return [('fit_moments_kernel', e0, e1), ('fit_backward_kernel', e1, e2)]
 
-    for _ in range(args.warmup):
-        step()
-    torch.cuda.synchronize()
+    for attempt in range(2):
+        ok = torch.ones(1, device=dev)
+        try:
+            for _ in range(args.warmup):
+                step()
+            torch.cuda.synchronize()
+        except Exception as e:      # noqa: BLE001
+            if gather_mode != 'peer':
+                raise
+            print('bench: peer-memory gather failed in warm-up (%s), using NCCL' % str(e).splitlines()[0], file=sys.stderr)
+            ok.zero_()
+        if world > 1:
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if float(ok) == 1.0:
+            break
+        peer, gather_mode = None, 'sync'
     if world > 1:
         dist.barrier()
     launches0 = lib.posefit_launch_count()
@@ -520,9 +552,12 @@ def run_ours(args):
             'config': {'workload': workload_name(n_obj, size),
                        'objects_per_gpu': n_obj, 'crop': [size, size],
                        'l2': 'inputs per step (%.1f GB) exceed the 126 MB L2; no flush needed' % (n_obj * 17 * P / 1e9),
-                       'collective': (('all_gather of 128-B pose records per step, ' +
-                                       ('queued beside the backward pass' if gather_async else 'after the backward pass'))
-                                      if world > 1 else 'none'),
+                       'collective': {'none': 'none',
+                                      'peer': 'all-gather of 128-B pose records per step over NVLink peer memory '
+                                              '(symmetric memory, copy engines) beside the backward pass',
+                                      'sync': 'NCCL all_gather of 128-B pose records per step, after the backward pass',
+                                      'async': 'NCCL all_gather of 128-B pose records per step, beside the backward pass'
+                                      }[gather_mode],
                        'host_numa_node': numa_node},
             'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': int(launches),
             'clocks': clk.summary(), 'configs': configs,

@@ -1,7 +1,6 @@
-for cfg in "12 4" "14 4" "14 6" "13 6" "12 6" "15 4" "12 4"; do
-set -- $cfg
-POSEFIT_SMALL_WARPS=$1 POSEFIT_DEPTH=$2 timeout 200 python bench.py --steps 3 --warmup 3 --no-cpu 2>/dev/null | python -c "
+for mode in peer sync; do
+POSEFIT_BENCH_GATHER=$mode timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 8 --steps 50 --warmup 5 --no-cpu --no-extra 2>gpurun_out/s22_$mode.err > gpurun_out/s22_n8_$mode.json; python -c "
 import json,sys
-d=json.loads(sys.stdin.read().strip().splitlines()[-1]); c=d['configs']
-print('warps $1 depth $2:', ' '.join('%s %.4f' % (k.split()[0], v['ms']) for k,v in c.items()))"
+d=json.loads(open('gpurun_out/s22_n8_$mode.json').read().strip().splitlines()[-1]); k=d['roofline']['kernels']; print('$mode', 'ms/step %.3f'%d['ms_per_step'], 'value %.3e'%d['value'], 'bwd %.3f' % k['fit_backward_kernel']['ms'], d['clocks']['sm_mhz'], 'e2e %.3e' % d['e2e']['value'], d['config']['collective'][:40])"
+grep "bench:" gpurun_out/s22_$mode.err | head -2
 done
