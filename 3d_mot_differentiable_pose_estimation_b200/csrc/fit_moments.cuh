@@ -35,6 +35,20 @@ constexpr int kChunkBytes = 2176; // one warp's chunk in shared memory: 4 float4
 __device__ __forceinline__ void cp_async_16(void* dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
+// variants taking the 32-bit shared-window address directly (no generic -> shared conversion per copy)
+__device__ __forceinline__ void cp_async_16_s(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_4_s(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+// x & m on the raw bits, opaque to the optimiser: masking the FLOAT (one instruction) instead of the converted
+// double (the compiler otherwise moves the select behind the conversion: two FSELs per value)
+__device__ __forceinline__ float and_bits(float x, uint32_t m) {
+  uint32_t r;
+  asm("and.b32 %0, %1, %2;" : "=r"(r) : "r"(__float_as_uint(x)), "r"(m));
+  return __uint_as_float(r);
+}
 template <int N>
 __device__ __forceinline__ void cp_async_wait_group() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
@@ -44,17 +58,20 @@ __device__ __forceinline__ void cp_async_wait_group() {
 // completion tracked per thread by cp.async groups).  Every lane reads back only what it requested
 // itself, so the per-warp ring needs no barrier at all.  n0 / dz / mk point at this lane's first
 // pixel in the NOC plane 0, the depth crop and the mask crop.
-template <bool VEC>
-__device__ __forceinline__ void request_chunk(unsigned char* stage, const float* n0, const float* dz,
+// VEC: 0 = ragged shapes / unaligned pointers, 1 = 128-bit copies (P % 4 == 0, aligned bases), 2 = as 1 and
+// every chunk is full (P % 128 == 0: no end-of-object tests).  stage_s = shared-window address of `stage`.
+template <int VEC>
+__device__ __forceinline__ void request_chunk(unsigned char* stage, uint32_t stage_s, const float* n0, const float* dz,
                                               const uint8_t* mk, int P, int px, int lane) {
-  if (px >= P) return;
+  if (VEC != 2 && px >= P) return;
   unsigned char* s = stage + lane * 16;
-  if (VEC) {                                                 // P % 4 == 0 and 16-byte aligned bases
-    cp_async_16(s, n0);
-    cp_async_16(s + 512, n0 + P);
-    cp_async_16(s + 1024, n0 + 2 * (size_t)P);
-    cp_async_16(s + 1536, dz);
-    cp_async_4(stage + 2048 + lane * 4, mk);
+  if (VEC != 0) {
+    const uint32_t s32 = stage_s + lane * 16;
+    cp_async_16_s(s32, n0);
+    cp_async_16_s(s32 + 512, n0 + P);
+    cp_async_16_s(s32 + 1024, n0 + 2 * (size_t)P);
+    cp_async_16_s(s32 + 1536, dz);
+    cp_async_4_s(stage_s + 2048 + lane * 4, mk);
   } else {
     // ragged shapes / unaligned pointers: 4-byte copies for the floats, plain byte loads for the mask
     unsigned char mm[4] = {0, 0, 0, 0};
@@ -132,7 +149,7 @@ struct LaneSums {
   }
 };
 
-template <bool POINTS, int DEPTH, bool VEC>
+template <bool POINTS, int DEPTH, int VEC>
 __global__ void __launch_bounds__(512, 1) fit_moments_kernel(const FwdParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -163,6 +180,7 @@ __global__ void __launch_bounds__(512, 1) fit_moments_kernel(const FwdParams p) 
   int row = 0, col = 0;                                       // of this lane's first pixel in the chunk
   const int drow = kChunkPx / p.W, dcol = kChunkPx % p.W;
   const bool row_fast = (p.W % 4 == 0);                       // a lane's 4 pixels never straddle a row
+  bool fast_px = false;                                       // row_fast and a pinhole K (set per object)
 
   auto write_part = [&](int o) {
     double out[kAccPlain];
@@ -178,6 +196,7 @@ __global__ void __launch_bounds__(512, 1) fit_moments_kernel(const FwdParams p) 
   // request stream: runs DEPTH-1 chunks ahead of the consumer; running pointers, no per-chunk
   // address arithmetic beyond three increments
   const int P = p.P;
+  const uint32_t ring_s = smem_u32(ring);
   int q_left = n_chunks, q_obj = obj, q_ch = ch, q_slot = 0;
   int q_px = ch * kChunkPx + 4 * lane;
   const float* q_n0 = p.noc + (size_t)obj * 3 * P + q_px;
@@ -185,7 +204,7 @@ __global__ void __launch_bounds__(512, 1) fit_moments_kernel(const FwdParams p) 
   const uint8_t* q_mk = p.mask + (size_t)obj * P + q_px;
   auto request_next = [&]() {
     if (q_left > 0) {
-      request_chunk<VEC>(ring + q_slot * kChunkBytes, q_n0, q_dz, q_mk, P, q_px, lane);
+      request_chunk<VEC>(ring + q_slot * kChunkBytes, ring_s + q_slot * kChunkBytes, q_n0, q_dz, q_mk, P, q_px, lane);
       --q_left;
       if (++q_slot == DEPTH) q_slot = 0;
       if (++q_ch == cpo) {
@@ -225,6 +244,7 @@ __global__ void __launch_bounds__(512, 1) fit_moments_kernel(const FwdParams p) 
         g.x0 = p.bbox[2 * (size_t)obj];
         g.y0 = p.bbox[2 * (size_t)obj + 1];
         g.simple = (K[1] == 0.0 && K[3] == 0.0 && K[6] == 0.0 && K[7] == 0.0 && K[8] == 1.0);
+        fast_px = row_fast && g.simple;
         __syncwarp();
         build_ray_tables(p, g, rxc, ryr, lane, 32);
         __syncwarp();
@@ -248,19 +268,19 @@ __global__ void __launch_bounds__(512, 1) fit_moments_kernel(const FwdParams p) 
     } else {
       cp_async_wait_group<DEPTH - 1>();                       // this lane's copies of this chunk have landed
       const unsigned char* st = ring + slot * kChunkBytes + lane * 16;
-      uchar4 m4 = make_uchar4(0, 0, 0, 0);
+      uint32_t m4 = 0u;                                       // 4 mask bytes
       float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (px0 < P) {
-        m4 = *reinterpret_cast<const uchar4*>(ring + slot * kChunkBytes + 2048 + lane * 4);
+      const bool in_obj = (VEC == 2) || px0 < P;              // VEC == 2: every chunk is full
+      if (in_obj) {
+        m4 = *reinterpret_cast<const uint32_t*>(ring + slot * kChunkBytes + 2048 + lane * 4);
         z4 = *reinterpret_cast<const float4*>(st + 1536);
       }
       const float zz[4] = {z4.x, z4.y, z4.z, z4.w};
-      const unsigned char mm[4] = {m4.x, m4.y, m4.z, m4.w};
       bool ok[4];
       bool any = false;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {                           // pose_estimation.py:23-25
-        ok[j] = mm[j] != 0 && zz[j] > 0.0f && (VEC || px0 + j < P);
+        ok[j] = (m4 & (0xffu << (8 * j))) != 0u && zz[j] > 0.0f && (VEC != 0 || px0 + j < P);
         any = any || ok[j];
       }
       if (__any_sync(0xffffffffu, any)) {
@@ -270,21 +290,25 @@ __global__ void __launch_bounds__(512, 1) fit_moments_kernel(const FwdParams p) 
         const float n0[4] = {a4.x, a4.y, a4.z, a4.w};
         const float n1[4] = {b4.x, b4.y, b4.z, b4.w};
         const float n2[4] = {c4.x, c4.y, c4.z, c4.w};
-        if (row_fast && g.simple) {
+        if (fast_px) {
           // lanes past the end of the object (last, partial chunk) carry zeros: keep their table reads
           // inside the tables (with a narrow crop `row` would run far past H, out of the CTA's shared memory)
-          const int trow = px0 < P ? row : 0, tcol = px0 < P ? col : 0;
+          const int trow = in_obj ? row : 0, tcol = in_obj ? col : 0;
           const double nry = -ryr[trow];
           const double2 rxa = *reinterpret_cast<const double2*>(rxc + tcol);
           const double2 rxb = *reinterpret_cast<const double2*>(rxc + tcol + 2);
           const double rx[4] = {rxa.x, rxa.y, rxb.x, rxb.y};
 #pragma unroll
+          uint32_t okm[4];                                    // all ones / zero per pixel
+#pragma unroll
+          for (int j = 0; j < 4; ++j) okm[j] = ok[j] ? 0xffffffffu : 0u;
+          acc.cnt -= (int)(okm[0] + okm[1]) + (int)(okm[2] + okm[3]);   // each valid pixel contributes -(-1)
+#pragma unroll
           for (int j = 0; j < 4; ++j) {                       // branch-free: invalid pixels contribute zeros
-            const double zd = (double)(ok[j] ? zz[j] : 0.0f);
-            const double a0 = (double)(ok[j] ? n0[j] : 0.0f);
-            const double a1 = (double)(ok[j] ? n1[j] : 0.0f);
-            const double a2 = (double)(ok[j] ? n2[j] : 0.0f);
-            acc.cnt += ok[j] ? 1 : 0;
+            const double zd = (double)and_bits(zz[j], okm[j]);
+            const double a0 = (double)and_bits(n0[j], okm[j]);
+            const double a1 = (double)and_bits(n1[j], okm[j]);
+            const double a2 = (double)and_bits(n2[j], okm[j]);
             acc.add(a0, a1, a2, rx[j] * zd, nry * zd, zd);    // y = (rx z, -ry z, [-]z), :34-41
           }
         } else {
