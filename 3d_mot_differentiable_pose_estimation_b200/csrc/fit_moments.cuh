@@ -298,7 +298,6 @@ __global__ void __launch_bounds__(512, 1) fit_moments_kernel(const FwdParams p) 
           const double2 rxa = *reinterpret_cast<const double2*>(rxc + tcol);
           const double2 rxb = *reinterpret_cast<const double2*>(rxc + tcol + 2);
           const double rx[4] = {rxa.x, rxa.y, rxb.x, rxb.y};
-#pragma unroll
           uint32_t okm[4];                                    // all ones / zero per pixel
 #pragma unroll
           for (int j = 0; j < 4; ++j) okm[j] = ok[j] ? 0xffffffffu : 0u;

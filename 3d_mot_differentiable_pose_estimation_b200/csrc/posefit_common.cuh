@@ -78,6 +78,8 @@ struct FwdParams {
   int B, H, W, P;
   int n_hyp, n_samp, ref_compat;
   int no_fast;                  // debugging: force the generic per-pixel passes of the RANSAC kernel
+  int no_idx_preload;           // debugging: per-sample index loads in the RANSAC gather loop
+  int no_early_issue;           // debugging: request every crop at the top of its own iteration
   int global_tile;              // RANSAC kernel: crop too large for shared memory, passes read global memory
   int tile_px, tiles_per_obj;   // a tile = tile_px consecutive pixels (whole rows in crop mode)
   int n_stages, tma_ok;
