@@ -102,34 +102,18 @@ class BatchedPoses(NamedTuple):
     scale: torch.Tensor          # [B]     camera-space fit, connected to autograd when pred_nocs requires grad:
     rot: torch.Tensor            # [B,3,3] the TRUE rotation (object -> camera is [s R | t], pose_estimation.py:401-403)
     trans: torch.Tensor          # [B,3]
+    # per launch group -- ONE group (plain tensors) unless `bucket` is given, then lists with one entry per group:
     raw: object                  # PoseFitRaw of the fit (float64 records, inlier mask, winners)
-    noc: torch.Tensor            # [B,3,H,W] resampled NOC crops (differentiable w.r.t. the head output)
-    crops: Crops
-    mask: torch.Tensor           # [B,H,W] u8 correspondences that reached the fit (after the pre-filters)
+    noc: object                  # [Bg,3,H,W] resampled NOC crops (differentiable w.r.t. the head output)
+    crops: object                # Crops
+    mask: object                 # [Bg,H,W] u8 correspondences that reached the fit (after the pre-filters)
+    group_index: Optional[list] = None   # bucketed runs: instance indices (ascending) of every group
 
 
-def run_pose_batched(pred_nocs, depth_frames, inst_masks, boxes_xyxy, frame_of: Optional[torch.Tensor] = None,
-                     campose=None, kinv=None, gt_boxes=None, ransac: bool = True, n_iterations: int = 100,
-                     n_samples: int = 10, apply_statistical_filter: bool = True, sample_idx=None,
-                     height: Optional[int] = None, width: Optional[int] = None) -> BatchedPoses:
-    """The per-instance loop of `postprocess_dets` (Detection/tracker/postprocess.py:131-165) -- roi_align of
-    the NOC head output, depth / mask slicing, run_pose -- for ALL instances of a batch of frames at once.
-
-    pred_nocs [B,3,Hh,Wh] head outputs; depth_frames [F,FH,FW]; inst_masks [B,FH,FW]; boxes_xyxy [B,4];
-    frame_of [B] frame index of each instance (None: one frame); campose [4,4] / [F,4,4] camera-to-world
-    (None keeps camera space, as run_pose_office); gt_boxes [B,8,3] enables the clean_depth clip (:293-299).
-    RANSAC indices are drawn from the global `np.random` stream exactly as the per-instance drop-in does
-    (instance after instance, `randint(N_i, size=(n_iterations, n_samples))`, nothing for an empty instance)
-    unless `sample_idx` [B,n_hyp,n_samp] is given; the only host round trip is the B correspondence counts
-    that `randint` needs.  Instances are padded to one H x W (default: the largest box, width rounded up to 4)."""
-    import numpy as np
-    from .function import (PoseFitFull, PoseFitRaw, pose_epilogue, clip_mask_to_box, statistical_outlier_mask)
-    boxes = torch.as_tensor(boxes_xyxy)
-    if height is None or width is None:
-        bh = int((boxes[:, 3] - boxes[:, 1]).max()) if boxes.numel() else 1
-        bw = int((boxes[:, 2] - boxes[:, 0]).max()) if boxes.numel() else 1
-        height = height or max(bh, 1)
-        width = width or max((bw + 3) // 4 * 4, 4)
+def _prepare(pred_nocs, depth_frames, inst_masks, boxes, frame_of, campose, kinv, gt_boxes, apply_statistical_filter,
+             height, width):
+    """gather -> resample -> GT clip -> the two outlier filters, for instances that share one H x W canvas."""
+    from .function import clip_mask_to_box, statistical_outlier_mask
     crops = gather_crops(depth_frames, inst_masks, boxes, frame_of, height, width)
     noc = resample_noc(pred_nocs, crops.roi_hw, height, width)
     mask = crops.mask
@@ -139,13 +123,21 @@ def run_pose_batched(pred_nocs, depth_frames, inst_masks, boxes_xyxy, frame_of: 
     if apply_statistical_filter:
         mask = statistical_outlier_mask(None, crops.depth, mask, crops.bbox_xy0, kinv, source='depth')
         mask = statistical_outlier_mask(noc.detach(), crops.depth, mask, crops.bbox_xy0, kinv, source='noc')
-    if ransac and sample_idx is None:
-        counts = ((mask != 0) & (crops.depth > 0)).flatten(1).sum(1).cpu().numpy()     # the one host round trip
-        idx = np.zeros((len(counts), n_iterations, n_samples), dtype=np.int32)
-        for i, n in enumerate(counts):
-            if n > 0:
-                idx[i] = np.random.randint(int(n), size=(n_iterations, n_samples))     # pose_utils.py:73
-        sample_idx = torch.from_numpy(idx)
+    return crops, noc, mask, cam_index
+
+
+def _draw_sample_idx(counts, n_iterations: int, n_samples: int) -> torch.Tensor:
+    """The reference's draws (pose_utils.py:73), instance after instance, nothing for an empty instance."""
+    import numpy as np
+    idx = np.zeros((len(counts), n_iterations, n_samples), dtype=np.int32)
+    for i, n in enumerate(counts):
+        if n > 0:
+            idx[i] = np.random.randint(int(n), size=(n_iterations, n_samples))
+    return torch.from_numpy(idx)
+
+
+def _fit(noc, crops, mask, kinv, campose, cam_index, sample_idx, ransac):
+    from .function import PoseFitFull, PoseFitRaw, pose_epilogue
     # one forward feeds both autograd (the reference detaches here, postprocess.py:151; we do not have to) and the epilogue
     scale, rot, trans, inl, status, n_valid, pose64, winner = PoseFitFull.apply(
         noc, crops.depth, mask, crops.bbox_xy0, kinv, sample_idx if ransac else None, 1.0, True)
@@ -153,3 +145,87 @@ def run_pose_batched(pred_nocs, depth_frames, inst_masks, boxes_xyxy, frame_of: 
     epi = pose_epilogue(raw, crops.depth, mask, crops.bbox_xy0, kinv, campose=campose, cam_index=cam_index)
     return BatchedPoses(epi.global_rot, epi.global_trans, epi.global_scale, epi.euler, epi.world_box, status,
                         scale, rot, trans, raw, noc, crops, mask)
+
+
+def _canvas(boxes: torch.Tensor):
+    bh = int((boxes[:, 3] - boxes[:, 1]).max()) if boxes.numel() else 1
+    bw = int((boxes[:, 2] - boxes[:, 0]).max()) if boxes.numel() else 1
+    return max(bh, 1), max((bw + 3) // 4 * 4, 4)
+
+
+def run_pose_batched(pred_nocs, depth_frames, inst_masks, boxes_xyxy, frame_of: Optional[torch.Tensor] = None,
+                     campose=None, kinv=None, gt_boxes=None, ransac: bool = True, n_iterations: int = 100,
+                     n_samples: int = 10, apply_statistical_filter: bool = True, sample_idx=None,
+                     height: Optional[int] = None, width: Optional[int] = None,
+                     bucket: Optional[int] = None) -> BatchedPoses:
+    """The per-instance loop of `postprocess_dets` (Detection/tracker/postprocess.py:131-165) -- roi_align of
+    the NOC head output, depth / mask slicing, run_pose -- for ALL instances of a batch of frames at once.
+
+    pred_nocs [B,3,Hh,Wh] head outputs; depth_frames [F,FH,FW]; inst_masks [B,FH,FW]; boxes_xyxy [B,4];
+    frame_of [B] frame index of each instance (None: one frame); campose [4,4] / [F,4,4] camera-to-world
+    (None keeps camera space, as run_pose_office); gt_boxes [B,8,3] enables the clean_depth clip (:293-299).
+    RANSAC indices are drawn from the global `np.random` stream exactly as the per-instance drop-in does
+    (instance after instance, `randint(N_i, size=(n_iterations, n_samples))`, nothing for an empty instance)
+    unless `sample_idx` [B,n_hyp,n_samp] is given; the only host round trip is the B correspondence counts
+    that `randint` needs.  Instances are padded to one H x W (default: the largest box, width rounded up to 4).
+
+    bucket=k: boxes of very different sizes make that padding the dominant traffic (a 24x24 box on a 160x200 canvas
+    reads 55x its own bytes).  With `bucket` the instances are grouped by box size rounded up to multiples of k and
+    every group runs on its own canvas (one launch sequence per group, still one host round trip and the same draw
+    order); the per-instance outputs come back in instance order, the per-group tensors (`raw`, `noc`, `crops`,
+    `mask`) as lists with `group_index` naming the instances of each group."""
+    boxes = torch.as_tensor(boxes_xyxy)
+    if bucket and int(boxes.shape[0]) > 0:
+        return _run_pose_bucketed(pred_nocs, depth_frames, inst_masks, boxes, frame_of, campose, kinv, gt_boxes, ransac,
+                                  n_iterations, n_samples, apply_statistical_filter, sample_idx, int(bucket))
+    if height is None or width is None:
+        ch, cw = _canvas(boxes)
+        height, width = height or ch, width or cw
+    crops, noc, mask, cam_index = _prepare(pred_nocs, depth_frames, inst_masks, boxes, frame_of, campose, kinv, gt_boxes,
+                                           apply_statistical_filter, height, width)
+    if ransac and sample_idx is None:
+        counts = ((mask != 0) & (crops.depth > 0)).flatten(1).sum(1).cpu().numpy()     # the one host round trip
+        sample_idx = _draw_sample_idx(counts, n_iterations, n_samples)
+    return _fit(noc, crops, mask, kinv, campose, cam_index, sample_idx, ransac)
+
+
+def _run_pose_bucketed(pred_nocs, depth_frames, inst_masks, boxes, frame_of, campose, kinv, gt_boxes, ransac,
+                       n_iterations, n_samples, apply_statistical_filter, sample_idx, bucket: int) -> BatchedPoses:
+    b = int(boxes.shape[0])
+    hw = torch.stack([boxes[:, 3] - boxes[:, 1], boxes[:, 2] - boxes[:, 0]], dim=1).cpu().clamp_(min=1)
+    key = (hw + bucket - 1) // bucket * bucket
+    key[:, 1] = (key[:, 1] + 3) // 4 * 4
+    groups = {}
+    for i in range(b):
+        groups.setdefault((int(key[i, 0]), int(key[i, 1])), []).append(i)
+    dev = pred_nocs.device
+
+    def take(t, idx):
+        return None if t is None else torch.as_tensor(t).to(dev)[idx]
+
+    per_object_kinv = kinv is not None and torch.as_tensor(kinv).dim() == 3
+    prepared = []
+    for (gh, gw), members in sorted(groups.items()):
+        idx = torch.tensor(members, dtype=torch.long, device=dev)
+        k_g = take(kinv, idx) if per_object_kinv else kinv
+        crops, noc, mask, cam_index = _prepare(pred_nocs[idx], depth_frames, take(inst_masks, idx), take(boxes, idx),
+                                               take(frame_of, idx), campose, k_g, take(gt_boxes, idx),
+                                               apply_statistical_filter, gh, gw)
+        prepared.append((idx, k_g, crops, noc, mask, cam_index))
+    if ransac and sample_idx is None:
+        counts = torch.zeros(b, dtype=torch.long, device=dev)
+        for idx, _, crops, _, mask, _ in prepared:
+            counts[idx] = ((mask != 0) & (crops.depth > 0)).flatten(1).sum(1)
+        sample_idx = _draw_sample_idx(counts.cpu().numpy(), n_iterations, n_samples)     # the one host round trip
+    if sample_idx is not None:
+        sample_idx = torch.as_tensor(sample_idx).to(dev)
+    parts = [_fit(noc, crops, mask, k_g, campose, cam_index, sample_idx[idx] if ransac else None, ransac)
+             for idx, k_g, crops, noc, mask, cam_index in prepared]
+    order = torch.cat([pr[0] for pr in prepared]) if prepared else torch.zeros(0, dtype=torch.long, device=dev)
+    inv = torch.argsort(order)
+
+    def merged(name):
+        return torch.cat([getattr(q, name) for q in parts])[inv]
+    fields = ('global_rot', 'global_trans', 'global_scale', 'euler', 'world_box', 'status', 'scale', 'rot', 'trans')
+    return BatchedPoses(*[merged(f) for f in fields], [q.raw for q in parts], [q.noc for q in parts],
+                        [q.crops for q in parts], [q.mask for q in parts], [pr[0] for pr in prepared])

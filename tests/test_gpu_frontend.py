@@ -181,3 +181,64 @@ def test_run_pose_batched_is_differentiable_to_the_head_output(pf):
     assert torch.isfinite(g1).all() and float(g1.abs().max()) > 0
     # (the resample adjoint accumulates with float atomics: equal up to summation order)
     assert float((g1 - head2.grad).abs().max()) <= 1e-5 * float(g1.abs().max())
+
+
+def test_run_pose_batched_bucketed_equals_single_canvas(pf):
+    """bucket=k groups the instances by box size (one canvas per group instead of padding everything to the largest
+    box): same draws, same statuses / winners / inlier decisions, poses equal to rounding, gradients to the head
+    output equal, per-instance outputs in instance order."""
+    rng = np.random.default_rng(21)
+    gen = torch.Generator().manual_seed(21)
+    FH, FW = 240, 320
+    boxes = np.array([[40, 30, 64, 50], [150, 60, 222, 110], [10, 150, 60, 214], [200, 120, 264, 180], [90, 90, 131, 123],
+                      [5, 5, 165, 125], [100, 10, 124, 33], [230, 20, 300, 100]], dtype=np.int32)
+    b = boxes.shape[0]
+    frame_of = np.array([0, 0, 1, 1, 0, 1, 0, 1], dtype=np.int32)
+    head = torch.rand(b, 3, 28, 28, generator=gen)
+    depth = np.zeros((2, FH, FW), dtype=np.float32)
+    masks = np.zeros((b, FH, FW), dtype=bool)
+    for i in range(b):
+        x0, y0, x1, y1 = boxes[i]
+        h, w = y1 - y0, x1 - x0
+        patch = _reference_patch(head[i], h, w).permute(1, 2, 0).numpy().astype(np.float64)
+        rot = np.linalg.qr(rng.normal(size=(3, 3)))[0]
+        rot *= np.sign(np.linalg.det(rot))
+        pts = 1.5 * (patch.reshape(-1, 3) - 0.5) @ rot.T + np.array([0.0, 0.0, -3.5])
+        z = (-pts[:, 2]).reshape(h, w) + rng.normal(scale=0.01, size=(h, w))
+        free = depth[frame_of[i], y0:y1, x0:x1] == 0
+        depth[frame_of[i], y0:y1, x0:x1] = np.where(free, z, depth[frame_of[i], y0:y1, x0:x1]).astype(np.float32)
+        masks[i, y0:y1, x0:x1] = (rng.uniform(size=(h, w)) < 0.8) & free
+    masks[6] = False                                                           # an empty instance
+    campose = np.tile(np.identity(4), (2, 1, 1))
+    for f in range(2):
+        campose[f, :3, :3] = np.linalg.qr(rng.normal(size=(3, 3)))[0]
+        campose[f, :3, 3] = rng.normal(size=3)
+    args = (torch.from_numpy(depth).cuda(), torch.from_numpy(masks).cuda(), torch.from_numpy(boxes).cuda(),
+            torch.from_numpy(frame_of).cuda())
+    outs = []
+    for bucket in (None, 32):
+        np.random.seed(77)
+        outs.append(pf.run_pose_batched(head.cuda(), *args, campose=torch.from_numpy(campose), bucket=bucket))
+    one, many = outs
+    assert len(many.group_index) > 2 and sorted(torch.cat(many.group_index).tolist()) == list(range(b))
+    assert one.status.tolist() == many.status.tolist() and int(one.status[6]) == 1
+    ok = (one.status == 0).cpu().numpy()
+    assert ok.sum() >= b - 2
+    for name in ('global_rot', 'global_trans', 'global_scale', 'world_box', 'euler'):
+        x, y = getattr(one, name).cpu().numpy()[ok], getattr(many, name).cpu().numpy()[ok]
+        np.testing.assert_allclose(y, x, rtol=1e-9, atol=1e-9, err_msg=name)
+    for g, idx in enumerate(many.group_index):                                 # winners and inlier masks, instance by instance
+        for j, i in enumerate(idx.tolist()):
+            assert int(many.raw[g].winner[j]) == int(one.raw.winner[i])
+            h, w = boxes[i, 3] - boxes[i, 1], boxes[i, 2] - boxes[i, 0]
+            assert torch.equal(many.raw[g].inlier_mask[j, :h, :w], one.raw.inlier_mask[i, :h, :w])
+    # gradients to the head output (plain fit, no filters: the differentiable configuration)
+    grads = []
+    w_s, w_r, w_t = torch.randn(b, device='cuda'), torch.randn(b, 3, 3, device='cuda'), torch.randn(b, 3, device='cuda')
+    for bucket in (None, 32):
+        hd = head.cuda().requires_grad_(True)
+        o = pf.run_pose_batched(hd, *args, ransac=False, apply_statistical_filter=False, bucket=bucket)
+        ((o.scale * w_s).sum() + (o.rot * w_r).sum() + (o.trans * w_t).sum()).backward()
+        grads.append(hd.grad.clone())
+    assert torch.isfinite(grads[0]).all() and float(grads[0].abs().max()) > 0
+    assert float((grads[0] - grads[1]).abs().max()) <= 1e-5 * float(grads[0].abs().max())
