@@ -12,7 +12,8 @@ import subprocess
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libposefit_b200.so')
+# POSEFIT_LIB: tooling only (A/B runs of experimental builds, tools/ransac_phases.py); the product is the in-tree library
+LIB_PATH = os.environ.get('POSEFIT_LIB') or os.path.join(_HERE, 'libposefit_b200.so')
 CSRC = os.path.join(_HERE, 'csrc')
 
 POSE_DOUBLES = 16
