@@ -36,8 +36,13 @@ def compare(raw, ora, ransac, tag, sample_idx=None):
     inl = raw.inlier_mask.cpu().numpy() if raw.inlier_mask is not None else None
     worst = 0.0
     for i, o in enumerate(ora):
-        assert status[i] == o['status'], (tag, 'status', i, int(status[i]), o['status'])
         assert n_valid[i] == o['n_valid'], (tag, 'n_valid', i)
+        if ransac and 0 < o['n_valid'] < 3:
+            # one or two correspondences: EVERY hypothesis has a rank <= 1 covariance, the rotation (and with it the
+            # inlier ratio gate) is LAPACK's arbitrary choice -- nothing to compare beyond the count
+            ties[0] += 1
+            continue
+        assert status[i] == o['status'], (tag, 'status', i, int(status[i]), o['status'])
         tie = False
         if ransac and 'residuals' in o:
             # two hypotheses whose residuals agree to the last bits (the same samples drawn in another order)
