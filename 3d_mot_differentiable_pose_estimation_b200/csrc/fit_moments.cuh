@@ -149,8 +149,13 @@ struct LaneSums {
   }
 };
 
-template <bool POINTS, int DEPTH, int VEC>
+// PAIR (only with VEC == 2, an even number of chunks per object and per warp): two chunks per loop iteration --
+// one set of request / object / ring bookkeeping per 256 pixels, the second chunk addressed by immediate
+// offsets.  The per-chunk overhead (a third of the loop's instructions) is what makes this kernel issue-limited
+// when the board's power cap lowers the SM clock.
+template <bool POINTS, int DEPTH, int VEC, bool PAIR = false>
 __global__ void __launch_bounds__(512, 1) fit_moments_kernel(const FwdParams p) {
+  static_assert(!PAIR || (!POINTS && VEC == 2 && DEPTH % 2 == 0 && DEPTH >= 4), "PAIR: full aligned chunks, even ring");
   extern __shared__ __align__(128) unsigned char smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   unsigned char* ring = smem + (size_t)warp * p.warp_smem_bytes;               // DEPTH stages of kChunkBytes
@@ -223,13 +228,132 @@ __global__ void __launch_bounds__(512, 1) fit_moments_kernel(const FwdParams p) 
     }
     cp_async_commit();
   };
+  int slot = 0;
+  int px0 = ch * kChunkPx + 4 * lane;
+  if constexpr (PAIR) {
+    auto request_pair = [&]() {
+      if (q_left > 0) {
+        const uint32_t sa = ring_s + q_slot * kChunkBytes + lane * 16;           // slot A; slot B follows it
+        cp_async_16_s(sa, q_n0);
+        cp_async_16_s(sa + kChunkBytes, q_n0 + kChunkPx);
+        cp_async_16_s(sa + 512, q_n0 + P);
+        cp_async_16_s(sa + kChunkBytes + 512, q_n0 + P + kChunkPx);
+        cp_async_16_s(sa + 1024, q_n0 + 2 * (size_t)P);
+        cp_async_16_s(sa + kChunkBytes + 1024, q_n0 + 2 * (size_t)P + kChunkPx);
+        cp_async_16_s(sa + 1536, q_dz);
+        cp_async_16_s(sa + kChunkBytes + 1536, q_dz + kChunkPx);
+        const uint32_t ma = ring_s + q_slot * kChunkBytes + 2048 + lane * 4;
+        cp_async_4_s(ma, q_mk);
+        cp_async_4_s(ma + kChunkBytes, q_mk + kChunkPx);
+        q_left -= 2;
+        q_slot += 2;
+        if (q_slot == DEPTH) q_slot = 0;
+        q_ch += 2;
+        if (q_ch == cpo) {
+          q_ch = 0;
+          ++q_obj;
+          q_n0 = p.noc + (size_t)q_obj * 3 * P + 4 * lane;
+          q_dz = p.depth + (size_t)q_obj * P + 4 * lane;
+          q_mk = p.mask + (size_t)q_obj * P + 4 * lane;
+        } else {
+          q_n0 += 2 * kChunkPx;
+          q_dz += 2 * kChunkPx;
+          q_mk += 2 * kChunkPx;
+        }
+      }
+      cp_async_commit();
+    };
+#pragma unroll
+    for (int i = 0; i < DEPTH / 2 - 1; ++i) request_pair();
+    for (int it = 0; it < n_chunks; it += 2) {
+      request_pair();                                           // refills the two stages consumed last iteration
+      if (obj != cur_obj) {
+        if (cur_obj >= 0) write_part(cur_obj);
+        cur_obj = obj;
+        acc.clear();
+        const double* K = p.kinv + (p.kinv_per_object ? 9 * (size_t)obj : 0);
+        g.k = K;
+        g.k0 = K[0]; g.k2 = K[2]; g.k4 = K[4]; g.k5 = K[5];
+        g.x0 = p.bbox[2 * (size_t)obj];
+        g.y0 = p.bbox[2 * (size_t)obj + 1];
+        g.simple = (K[1] == 0.0 && K[3] == 0.0 && K[6] == 0.0 && K[7] == 0.0 && K[8] == 1.0);
+        fast_px = row_fast && g.simple;
+        __syncwarp();
+        build_ray_tables(p, g, rxc, ryr, lane, 32);
+        __syncwarp();
+        row = px0 / p.W;
+        col = px0 - row * p.W;
+      }
+      cp_async_wait_group<DEPTH / 2 - 1>();                     // this lane's copies of both chunks have landed
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const unsigned char* st = ring + (slot + u) * kChunkBytes + lane * 16;
+        const uint32_t m4 = *reinterpret_cast<const uint32_t*>(ring + (slot + u) * kChunkBytes + 2048 + lane * 4);
+        const float4 z4 = *reinterpret_cast<const float4*>(st + 1536);
+        const float zz[4] = {z4.x, z4.y, z4.z, z4.w};
+        bool ok[4];
+        bool any = false;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {                           // pose_estimation.py:23-25
+          ok[j] = (m4 & (0xffu << (8 * j))) != 0u && zz[j] > 0.0f;
+          any = any || ok[j];
+        }
+        if (__any_sync(0xffffffffu, any)) {
+          const float4 a4 = *reinterpret_cast<const float4*>(st);
+          const float4 b4 = *reinterpret_cast<const float4*>(st + 512);
+          const float4 c4 = *reinterpret_cast<const float4*>(st + 1024);
+          const float n0[4] = {a4.x, a4.y, a4.z, a4.w};
+          const float n1[4] = {b4.x, b4.y, b4.z, b4.w};
+          const float n2[4] = {c4.x, c4.y, c4.z, c4.w};
+          if (fast_px) {
+            const double nry = -ryr[row];
+            const double2 rxa = *reinterpret_cast<const double2*>(rxc + col);
+            const double2 rxb = *reinterpret_cast<const double2*>(rxc + col + 2);
+            const double rx[4] = {rxa.x, rxa.y, rxb.x, rxb.y};
+            uint32_t okm[4];                                    // all ones / zero per pixel
+#pragma unroll
+            for (int j = 0; j < 4; ++j) okm[j] = ok[j] ? 0xffffffffu : 0u;
+            acc.cnt -= (int)(okm[0] + okm[1]) + (int)(okm[2] + okm[3]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {                       // branch-free: invalid pixels contribute zeros
+              const double zd = (double)and_bits(zz[j], okm[j]);
+              const double a0 = (double)and_bits(n0[j], okm[j]);
+              const double a1 = (double)and_bits(n1[j], okm[j]);
+              const double a2 = (double)and_bits(n2[j], okm[j]);
+              acc.add(a0, a1, a2, rx[j] * zd, nry * zd, zd);    // y = (rx z, -ry z, [-]z), :34-41
+            }
+          } else {
+            int r = row, cc = col;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (ok[j]) {
+                double y0, y1, y2;
+                backproject_px(g, rxc, ryr, r, cc, (double)zz[j], y0, y1, y2);
+                acc.add((double)n0[j], (double)n1[j], (double)n2[j], y0, y1, -y2);
+                ++acc.cnt;
+              }
+              if (++cc >= p.W) { cc = 0; ++r; }
+            }
+          }
+        }
+        row += drow;
+        col += dcol;
+        if (col >= p.W) { col -= p.W; ++row; }
+      }
+      px0 += 2 * kChunkPx;
+      ch += 2;
+      if (ch == cpo) { ch = 0; ++obj; px0 = 4 * lane; }
+      slot += 2;
+      if (slot == DEPTH) slot = 0;
+    }
+    write_part(cur_obj);
+    return;
+  }
   if (!POINTS) {
 #pragma unroll
     for (int i = 0; i < DEPTH - 1; ++i) request_next();
   }
 
-  int slot = 0;
-  int px0 = ch * kChunkPx + 4 * lane;
   for (int it = 0; it < n_chunks; ++it) {
     if (!POINTS) request_next();                              // refill the stage consumed last iteration
 

@@ -321,8 +321,8 @@ def test_tma_and_fallback_loaders_agree(pf, monkeypatch):
 
 
 def test_launch_variants_agree(pf, monkeypatch):
-    """Every launch-time knob of the library (CTA size of the RANSAC kernel, ring depth / vector loads / PDL /
-    warm-up pass of the plain path) selects a different kernel instantiation or schedule, never a different
+    """Every launch-time knob of the library (CTA size of the RANSAC kernel, its index preload and early crop request,
+    ring depth / vector loads / paired chunks / warps per CTA / PDL / warm-up pass of the plain path) selects a different kernel instantiation or schedule, never a different
     result: masks, winners and statuses identical, poses to rounding."""
     d = pf.synth.make_objects(48, 64, 64, seed=23, n_hyp=64)
     t = _cuda(d)
@@ -339,7 +339,10 @@ def test_launch_variants_agree(pf, monkeypatch):
     variants = [{'POSEFIT_RANSAC_THREADS': '256'}, {'POSEFIT_RANSAC_THREADS': '256', 'POSEFIT_RANSAC_MINB': '3'},
                 {'POSEFIT_RANSAC_CTAS_PER_SM': '1'}, {'POSEFIT_NO_VEC': '1'}, {'POSEFIT_DEPTH': '2'},
                 {'POSEFIT_DEPTH': '4'}, {'POSEFIT_NO_PDL': '1'}, {'POSEFIT_PREWARM': '0'}, {'POSEFIT_PREWARM': '1'},
-                {'POSEFIT_EARLY_DEP': '0'}, {'POSEFIT_EARLY_DEP': '15'}, {'POSEFIT_CTAS_PER_SM': '2'}]
+                {'POSEFIT_EARLY_DEP': '0'}, {'POSEFIT_EARLY_DEP': '15'}, {'POSEFIT_CTAS_PER_SM': '2'},
+                {'POSEFIT_PAIR': '0'}, {'POSEFIT_PAIR': '1', 'POSEFIT_DEPTH': '6'}, {'POSEFIT_SMALL_WARPS': '12'},
+                {'POSEFIT_SMALL_WARPS': '16', 'POSEFIT_PAIR': '1'}, {'POSEFIT_NO_IDX_PRELOAD': '1'},
+                {'POSEFIT_NO_EARLY_ISSUE': '1'}]
     for env in variants:
         for k, v in env.items():
             monkeypatch.setenv(k, v)
