@@ -189,15 +189,23 @@ def run_pose_batched(pred_nocs, depth_frames, inst_masks, boxes_xyxy, frame_of: 
     return _fit(noc, crops, mask, kinv, campose, cam_index, sample_idx, ransac)
 
 
-def _run_pose_bucketed(pred_nocs, depth_frames, inst_masks, boxes, frame_of, campose, kinv, gt_boxes, ransac,
-                       n_iterations, n_samples, apply_statistical_filter, sample_idx, bucket: int) -> BatchedPoses:
-    b = int(boxes.shape[0])
-    hw = torch.stack([boxes[:, 3] - boxes[:, 1], boxes[:, 2] - boxes[:, 0]], dim=1).cpu().clamp_(min=1)
+def bucket_groups(boxes_xyxy, bucket: int) -> dict:
+    """Instances grouped by canvas: {(H, W): [instance indices, ascending]} with H = box height rounded up to a
+    multiple of `bucket`, W = box width rounded up to a multiple of `bucket` and then of 4 (the vector loaders)."""
+    boxes = torch.as_tensor(boxes_xyxy).cpu().to(torch.int64)
+    hw = torch.stack([boxes[:, 3] - boxes[:, 1], boxes[:, 2] - boxes[:, 0]], dim=1).clamp_(min=1)
     key = (hw + bucket - 1) // bucket * bucket
     key[:, 1] = (key[:, 1] + 3) // 4 * 4
     groups = {}
-    for i in range(b):
+    for i in range(int(boxes.shape[0])):
         groups.setdefault((int(key[i, 0]), int(key[i, 1])), []).append(i)
+    return groups
+
+
+def _run_pose_bucketed(pred_nocs, depth_frames, inst_masks, boxes, frame_of, campose, kinv, gt_boxes, ransac,
+                       n_iterations, n_samples, apply_statistical_filter, sample_idx, bucket: int) -> BatchedPoses:
+    b = int(boxes.shape[0])
+    groups = bucket_groups(boxes, bucket)
     dev = pred_nocs.device
 
     def take(t, idx):

@@ -143,3 +143,27 @@ def test_numa_binding_helpers(tmp_path):
     before = os.sched_getaffinity(0)
     assert shard.bind_host_to_gpu(0, sysfs=str(tmp_path)) is None   # no CUDA device / no sysfs entry here
     assert os.sched_getaffinity(0) == before
+
+
+def test_bucket_groups_partition_the_instances():
+    """run_pose_batched(bucket=k): every instance lands in exactly one group whose canvas holds its box, widths are
+    multiples of 4, members stay in instance order (the RANSAC draws are made in that order)."""
+    import importlib
+    fe = importlib.import_module('3d_mot_differentiable_pose_estimation_b200.frontend')
+    rng = np.random.default_rng(3)
+    x0 = rng.integers(0, 200, size=40)
+    y0 = rng.integers(0, 150, size=40)
+    w = rng.integers(1, 120, size=40)
+    h = rng.integers(1, 90, size=40)
+    boxes = np.stack([x0, y0, x0 + w, y0 + h], axis=1).astype(np.int32)
+    boxes[7, 2:] = boxes[7, :2]                                   # a degenerate (empty) box still gets a 1-pixel canvas
+    for bucket in (1, 16, 32, 50):
+        groups = fe.bucket_groups(torch.from_numpy(boxes), bucket)
+        seen = sorted(i for members in groups.values() for i in members)
+        assert seen == list(range(40))
+        for (gh, gw), members in groups.items():
+            assert members == sorted(members) and gw % 4 == 0 and gh >= 1
+            for i in members:
+                bh, bw = max(boxes[i, 3] - boxes[i, 1], 1), max(boxes[i, 2] - boxes[i, 0], 1)
+                assert bh <= gh < bh + bucket and bw <= gw < bw + bucket + 4
+    assert len(fe.bucket_groups(torch.from_numpy(boxes), 1000)) == 1
