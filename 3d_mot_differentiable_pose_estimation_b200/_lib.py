@@ -26,7 +26,8 @@ SYMBOLS = ('posefit_version', 'posefit_error_string', 'posefit_workspace_bytes',
            'posefit_points_forward', 'posefit_points_forward_ransac', 'posefit_compact',
            'posefit_points_evaluate', 'posefit_transform_points', 'posefit_epilogue', 'posefit_clip_mask', 'posefit_sor_mask',
            'posefit_sor_workspace_bytes', 'posefit_resample_noc', 'posefit_resample_noc_backward',
-           'posefit_gather_crops', 'posefit_edge_features', 'posefit_edge_workspace_bytes')
+           'posefit_gather_crops', 'posefit_edge_features', 'posefit_edge_workspace_bytes',
+           'posefit_debug_reload_env')
 
 _lock = threading.Lock()
 _lib = None
@@ -64,6 +65,8 @@ def _declare(lib):
     lib.posefit_workspace_bytes.argtypes = [i32] * 5
     lib.posefit_launch_count.restype = c.c_ulonglong
     lib.posefit_launch_count.argtypes = []
+    lib.posefit_debug_reload_env.restype = None
+    lib.posefit_debug_reload_env.argtypes = []
     lib.posefit_forward.restype = i32
     lib.posefit_forward.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, sz, vp]
     lib.posefit_forward_ransac.restype = i32
@@ -122,6 +125,11 @@ def lib():
                     raise PoseFitError(f'ABI version mismatch: library {handle.posefit_version()}, binding {ABI_VERSION}')
                 _lib = handle
     return _lib
+
+
+def reload_knobs():
+    """Re-read the POSEFIT_* environment knobs (the library reads them once at load)."""
+    lib().posefit_debug_reload_env()
 
 
 def check(code: int, what: str):

@@ -80,6 +80,7 @@ struct FwdParams {
   int no_fast;                  // debugging: force the generic per-pixel passes of the RANSAC kernel
   int no_idx_preload;           // debugging: per-sample index loads in the RANSAC gather loop
   int no_early_issue;           // debugging: request every crop at the top of its own iteration
+  int no_screen;                // debugging: SCREEN kernel, but every hypothesis is fitted in double (= v1 arithmetic)
   int global_tile;              // RANSAC kernel: crop too large for shared memory, passes read global memory
   int tile_px, tiles_per_obj;   // a tile = tile_px consecutive pixels (whole rows in crop mode)
   int n_stages, tma_ok;

@@ -428,6 +428,138 @@ PF_HD double residual_sq(const GlobalStats& g, const double* A, const double* t)
   return acc + g.n * dd;
 }
 
+// ---------------------------------------------------------------------------------------------
+// fp32 SCREEN of a RANSAC hypothesis (fit_ransac_crop_kernel).
+//
+// The reference ranks the hypotheses by their total residual (pose_utils.py:76); only the winner's
+// transform is ever used.  Fitting all of them in double is what kept the RANSAC kernel latency-bound
+// (profiles/r01_n_*), so every hypothesis is first fitted in float -- same algorithm, one-sided Jacobi
+// start, no Newton polish -- and its residual is evaluated (in double, closed form) for that float
+// transform.  The float fit comes with an a-posteriori error estimate `rho` (relative error of the
+// transform: Newton residual and rounding of the covariance over the smallest eigenvalue of
+// L = tr(H) I - H, plus the rounding of the scale), from which the kernel derives an interval
+// [r2 - err, r2 + err] that contains the residual the double fit would give.  Only hypotheses whose
+// interval reaches below the smallest upper end (or below the stop threshold) are then fitted in
+// double by the very code the v1 kernel ran for all of them, so winner, transform and inlier mask are
+// bit-identical to a full double evaluation whenever the intervals hold; rho = +inf (degenerate or
+// ill-conditioned sample sets) forces the double fit.  tests/test_math_host.py checks the interval on
+// benchmark-like, clean, heavily contaminated, sparse and tiny clouds.
+// ---------------------------------------------------------------------------------------------
+struct ScreenFit {
+  float A[9];      // scoring transform (s * R^T when ref_compat, else s * R), row-major
+  float t[3];
+  float s;
+  float mx[3], my[3];   // sample means (unshifted)
+  float rho;       // relative error estimate of A and t's rotation part; +inf = not usable
+};
+
+constexpr float kScreenEps = 1.1920929e-7f;       // 2^-23
+
+// sums are over x - ox, y - oy (ox, oy = first sample), n = number of samples (the first included)
+PF_HD void screen_fit32(int n, const float* sx, const float* sy, const float* syx, float sxx, float syy,
+                        const float* ox, const float* oy, bool ref_compat, ScreenFit& f) {
+  const float inf = __builtin_huge_valf();
+  const float rn = 1.0f / (float)n;
+  float mux[3], muy[3], C[9];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) { mux[i] = sx[i] * rn; muy[i] = sy[i] * rn; }
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) C[3 * i + j] = syx[3 * i + j] * rn - muy[i] * mux[j];
+  const float ex = sxx * rn, ey = syy * rn;
+  const float var = ex - (mux[0] * mux[0] + mux[1] * mux[1] + mux[2] * mux[2]);
+  const float mag = pf_sqrt(ex * ey);               // >= every |syx| * rn (Cauchy-Schwarz)
+#pragma unroll
+  for (int i = 0; i < 3; ++i) { f.mx[i] = mux[i] + ox[i]; f.my[i] = muy[i] + oy[i]; }
+  float m = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) m = fmaxf(m, pf_abs(C[i]));
+  f.rho = inf;
+  f.s = 1.0f;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) f.A[i] = (i % 4 == 0) ? 1.0f : 0.0f;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) f.t[i] = f.my[i] - f.mx[i];
+  if (!(m > 1e-5f * mag) || !(mag < 1e30f) || !(var > 0.0f)) return;     // degenerate / non-finite: double decides
+  const float inv = 1.0f / m;
+  float a0[3], a1[3], a2[3], v0[3] = {1, 0, 0}, v1[3] = {0, 1, 0}, v2[3] = {0, 0, 1};
+#pragma unroll
+  for (int i = 0; i < 3; ++i) { a0[i] = C[3 * i] * inv; a1[i] = C[3 * i + 1] * inv; a2[i] = C[3 * i + 2] * inv; }
+#pragma unroll 1
+  for (int sweep = 0; sweep < 3; ++sweep) {
+    jacobi_pair(a0, a1, v0, v1);
+    jacobi_pair(a0, a2, v0, v2);
+    jacobi_pair(a1, a2, v1, v2);
+  }
+  float n0 = a0[0] * a0[0] + a0[1] * a0[1] + a0[2] * a0[2];
+  float n1 = a1[0] * a1[0] + a1[1] * a1[1] + a1[2] * a1[2];
+  float n2 = a2[0] * a2[0] + a2[1] * a2[1] + a2[2] * a2[2];
+  if (n0 < n1) { swap_cols(a0, a1); swap_cols(v0, v1); const float t = n0; n0 = n1; n1 = t; }
+  if (n0 < n2) { swap_cols(a0, a2); swap_cols(v0, v2); const float t = n0; n0 = n2; n2 = t; }
+  if (n1 < n2) { swap_cols(a1, a2); swap_cols(v1, v2); const float t = n1; n1 = n2; n2 = t; }
+  float u0[3], u1[3], u2[3], w2[3];
+  const float r0 = pf_rsqrt(n0);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) u0[i] = a0[i] * r0;
+  const float d = u0[0] * a1[0] + u0[1] * a1[1] + u0[2] * a1[2];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) u1[i] = a1[i] - d * u0[i];
+  const float l1 = u1[0] * u1[0] + u1[1] * u1[1] + u1[2] * u1[2];
+  if (!(l1 > 1e-6f * n0)) return;                   // (numerically) rank one: the rotation is not determined
+  const float r1 = pf_rsqrt(l1);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) u1[i] *= r1;
+  cross3(u0, u1, u2);
+  cross3(v0, v1, w2);
+  // signed third singular value u2^T C w2 = det(V) (u2 . C v2) and the smallest eigenvalue of L: sigma2 + sigma3
+  const float dv = w2[0] * v2[0] + w2[1] * v2[1] + w2[2] * v2[2];
+  const float s3 = (u2[0] * a2[0] + u2[1] * a2[1] + u2[2] * a2[2]) * dv;
+  const float s1 = n0 * r0, s2 = l1 * r1;
+  const float gap = s2 + s3;
+  if (!(gap > 3e-3f * s1)) return;                  // ill-conditioned rotation: double decides
+  float R[9];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) R[3 * i + j] = u0[i] * v0[j] + u1[i] * v1[j] + u2[i] * w2[j];
+  // M = R^T Cn: trace -> scale, skew part -> Newton residual of this start
+  float M[9];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      M[3 * i + j] = R[i] * (C[j] * inv) + R[3 + i] * (C[3 + j] * inv) + R[6 + i] * (C[6 + j] * inv);
+  const float trh = M[0] + M[4] + M[8];
+  const float kn = fmaxf(pf_abs(M[7] - M[5]), fmaxf(pf_abs(M[2] - M[6]), pf_abs(M[3] - M[1])));
+  if (!(trh > 0.0f)) return;
+  const float dc = 8.0f * kScreenEps * mag * inv;  // rounding of the (normalised) covariance entries
+  const float s = trh * m / var;                    // pose_utils.py:47-50 (var * trh != 0 here)
+  f.rho = (kn + dc) / gap + 3.0f * dc / trh + 8.0f * kScreenEps * ex / var;
+  f.s = s;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) f.A[3 * i + j] = s * (ref_compat ? R[3 * j + i] : R[3 * i + j]);
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+    f.t[i] = f.my[i] - s * (R[3 * i] * f.mx[0] + R[3 * i + 1] * f.mx[1] + R[3 * i + 2] * f.mx[2]);
+}
+
+// Half-width of the interval around r2 (the residual^2 of the float transform, evaluated in double) that
+// contains the residual^2 of the double fit: |d r2| <= 2 sqrt(r2) (|dA| sqrt(sum |x|^2) + |dt| sqrt(n)) to first
+// order; x_rms = sqrt(sum_i |x_i|^2 / n) over ALL correspondences.  The leading factor 2 is a safety margin on top of the
+// worst-case rounding constants (tests/test_math_host.py: no error above 5 % of the half-width on any regime).
+PF_HD double screen_interval(const ScreenFit& f, double r2, double n_all, double x_rms) {
+  if (!(f.rho < 1e30f) || !(r2 >= 0.0) || !(r2 < 1e300)) return __builtin_huge_val();
+  const double s = (double)pf_abs(f.s), rho = (double)f.rho;
+  const double amx = (double)(pf_abs(f.mx[0]) + pf_abs(f.mx[1]) + pf_abs(f.mx[2]));
+  const double amy = (double)(pf_abs(f.my[0]) + pf_abs(f.my[1]) + pf_abs(f.my[2]));
+  const double e8 = 8.0 * (double)kScreenEps;
+  const double lin = s * rho * (x_rms + amx) + e8 * (amy + s * amx);
+  return 2.0 * (2.0 * sqrt(r2 * n_all) * lin + n_all * lin * lin);
+}
+
 // Scoring transform of a fit.  ref_compat: A = s * R^T, the block the reference really builds
 // (pose_utils.py:58); otherwise the geometrically correct A = s * R.
 PF_HD void scoring_transform(const Fit& f, bool ref_compat, double* A) {

@@ -247,6 +247,11 @@ int posefit_edge_features(const double* translations, const double* rotations, c
  * gpu_launches claim). */
 unsigned long long posefit_launch_count(void);
 
+/* The POSEFIT_* launch knobs are read from the environment once, when the library is
+ * loaded.  Tests and tuning tools that change one afterwards call this to re-read them; the launch
+ * path itself never touches the environment. */
+void posefit_debug_reload_env(void);
+
 #ifdef __cplusplus
 }
 #endif

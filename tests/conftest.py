@@ -29,3 +29,28 @@ def pkg():
 @pytest.fixture(scope='session')
 def golden_dir():
     return GOLDEN
+
+
+class _Knobs:
+    """POSEFIT_* launch knobs: the library reads the environment once at load, so a test that flips one sets the
+    variable AND asks the library to re-read (posefit_debug_reload_env)."""
+
+    def __init__(self):
+        self.touched = set()
+
+    def set(self, name, value):
+        os.environ[name] = str(value)
+        self.touched.add(name)
+        load_pkg('_lib').reload_knobs()
+
+    def clear(self, *names):
+        for name in names or list(self.touched):
+            os.environ.pop(name, None)
+        load_pkg('_lib').reload_knobs()
+
+
+@pytest.fixture
+def knob():
+    k = _Knobs()
+    yield k
+    k.clear()

@@ -262,7 +262,7 @@ def test_ransac_sparse_masks_vs_oracle(pf):
         print('sparse ransac', (h, w), worst, n)
 
 
-def test_ransac_large_crops_global_mode(pf, monkeypatch):
+def test_ransac_large_crops_global_mode(pf, knob):
     """Boxes too large for the shared-memory staging (the reference takes any bbox up to the 240x320
     frame, pose_estimation.py:256-267) run the RANSAC kernel in its global-memory mode: against the
     oracle on 120x160 and frame-sized crops, and bit-identical masks/winners vs the staged mode on 64x64."""
@@ -277,7 +277,7 @@ def test_ransac_large_crops_global_mode(pf, monkeypatch):
     d = pf.synth.make_objects(16, 64, 64, seed=64, n_hyp=64)
     t = _cuda(d)
     a = pf.pose_fit_raw(t['noc'], t['depth'], t['mask'], t['bbox_xy0'], sample_idx=t['sample_idx'])
-    monkeypatch.setenv('POSEFIT_RANSAC_GLOBAL', '1')
+    knob.set('POSEFIT_RANSAC_GLOBAL', '1')
     g = pf.pose_fit_raw(t['noc'], t['depth'], t['mask'], t['bbox_xy0'], sample_idx=t['sample_idx'])
     torch.cuda.synchronize()
     assert torch.equal(a.inlier_mask, g.inlier_mask) and torch.equal(a.winner, g.winner)
@@ -294,7 +294,7 @@ def test_ransac_large_crops_global_mode(pf, monkeypatch):
         dst[i] = 1.3 * src[i] @ rot.T + np.array([0.1, 0.2, -3.0]) + rng.normal(scale=0.01, size=(n, 3))
         bad = rng.uniform(size=n) < 0.1
         dst[i, bad, 2] -= rng.uniform(25, 40, size=bad.sum())
-    monkeypatch.delenv('POSEFIT_RANSAC_GLOBAL')
+    knob.clear('POSEFIT_RANSAC_GLOBAL')
     rans = pf.points_fit_raw(torch.from_numpy(np.ascontiguousarray(src.transpose(0, 2, 1))).cuda(),
                              torch.from_numpy(np.ascontiguousarray(dst.transpose(0, 2, 1))).cuda(),
                              None, sample_idx=torch.from_numpy(idx).cuda())
@@ -307,12 +307,12 @@ def test_ransac_large_crops_global_mode(pf, monkeypatch):
         assert rot_err_deg(rans.pose[i, 1:10].cpu().numpy().reshape(3, 3), o['rot_t'].T) < 1e-7
 
 
-def test_tma_and_fallback_loaders_agree(pf, monkeypatch):
+def test_tma_and_fallback_loaders_agree(pf, knob):
     d = pf.synth.make_objects(24, 64, 64, seed=21, n_hyp=32)
     t = _cuda(d)
     a = pf.pose_fit_raw(t['noc'], t['depth'], t['mask'], t['bbox_xy0'])
     ar = pf.pose_fit_raw(t['noc'], t['depth'], t['mask'], t['bbox_xy0'], sample_idx=t['sample_idx'])
-    monkeypatch.setenv('POSEFIT_NO_TMA', '1')
+    knob.set('POSEFIT_NO_TMA', '1')
     b_ = pf.pose_fit_raw(t['noc'], t['depth'], t['mask'], t['bbox_xy0'])
     br = pf.pose_fit_raw(t['noc'], t['depth'], t['mask'], t['bbox_xy0'], sample_idx=t['sample_idx'])
     torch.cuda.synchronize()
@@ -320,7 +320,7 @@ def test_tma_and_fallback_loaders_agree(pf, monkeypatch):
     assert torch.equal(ar.inlier_mask, br.inlier_mask)
 
 
-def test_launch_variants_agree(pf, monkeypatch):
+def test_launch_variants_agree(pf, knob):
     """Every launch-time knob of the library (CTA size of the RANSAC kernel, its index preload and early crop request,
     ring depth / vector loads / paired chunks / warps per CTA / PDL / warm-up pass of the plain path) selects a different kernel instantiation or schedule, never a different
     result: masks, winners and statuses identical, poses to rounding."""
@@ -342,13 +342,15 @@ def test_launch_variants_agree(pf, monkeypatch):
                 {'POSEFIT_EARLY_DEP': '0'}, {'POSEFIT_EARLY_DEP': '15'}, {'POSEFIT_CTAS_PER_SM': '2'},
                 {'POSEFIT_PAIR': '0'}, {'POSEFIT_PAIR': '1', 'POSEFIT_DEPTH': '6'}, {'POSEFIT_SMALL_WARPS': '12'},
                 {'POSEFIT_SMALL_WARPS': '16', 'POSEFIT_PAIR': '1'}, {'POSEFIT_NO_IDX_PRELOAD': '1'},
-                {'POSEFIT_NO_EARLY_ISSUE': '1'}]
+                {'POSEFIT_NO_EARLY_ISSUE': '1'}, {'POSEFIT_RANSAC_SCREEN': '0'}, {'POSEFIT_NO_SCREEN': '1'},
+                {'POSEFIT_RANSAC_THREADS': '160'}, {'POSEFIT_RANSAC_THREADS': '192'},
+                {'POSEFIT_RANSAC_SCREEN': '0', 'POSEFIT_RANSAC_THREADS': '256'}]
     for env in variants:
         for k, v in env.items():
-            monkeypatch.setenv(k, v)
+            knob.set(k, v)
         plain, rans, gn = run()
         for k in env:
-            monkeypatch.delenv(k)
+            knob.clear(k)
         assert torch.equal(plain.status, base[0].status) and torch.equal(rans.status, base[1].status), env
         assert torch.equal(rans.inlier_mask, base[1].inlier_mask) and torch.equal(rans.winner, base[1].winner), env
         assert float((plain.pose[:, :13] - base[0].pose[:, :13]).abs().max()) < 1e-10, env
@@ -356,11 +358,11 @@ def test_launch_variants_agree(pf, monkeypatch):
         assert float((gn - base[2]).abs().max()) <= 1e-5 * float(base[2].abs().max()), env
 
 
-def test_ransac_fast_and_generic_passes_agree(pf, monkeypatch):
+def test_ransac_fast_and_generic_passes_agree(pf, knob):
     d = pf.synth.make_objects(64, 64, 64, seed=22, n_hyp=128)
     t = _cuda(d)
     a = pf.pose_fit_raw(t['noc'], t['depth'], t['mask'], t['bbox_xy0'], sample_idx=t['sample_idx'])
-    monkeypatch.setenv('POSEFIT_NO_FAST', '1')
+    knob.set('POSEFIT_NO_FAST', '1')
     b = pf.pose_fit_raw(t['noc'], t['depth'], t['mask'], t['bbox_xy0'], sample_idx=t['sample_idx'])
     torch.cuda.synchronize()
     assert torch.equal(a.inlier_mask, b.inlier_mask) and torch.equal(a.winner, b.winner)

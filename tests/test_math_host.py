@@ -225,3 +225,69 @@ def test_ransac_gradients_match_reference_finite_differences(golden_dir):
     assert np.abs(got_x - want_x).max() <= 2e-6 * np.abs(want_x).max()
     assert np.abs(got_z - want_z).max() <= 2e-6 * np.abs(want_z).max()
     assert np.all(want_x[wts == 0] == 0.0)                           # outliers of the winner: exactly no gradient
+
+
+# ---------------------------------------------------------------------------------------------
+# float screen of the RANSAC hypotheses (fit_ransac_kernel<.., SCREEN>): the residual interval of the float fit
+# must contain the double fit's residual, and the candidate rule must keep the reference's winner
+# ---------------------------------------------------------------------------------------------
+SCREEN_REGIMES = [
+    ('bench', dict(n=96, h=64, w=64, n_hyp=128, n_samp=10)),
+    ('clean', dict(n=48, h=64, w=64, n_hyp=128, n_samp=10, outlier_frac=0.0)),
+    ('no_noise', dict(n=24, h=64, w=64, n_hyp=64, n_samp=10, outlier_frac=0.0, noc_noise=0.0)),
+    ('heavy', dict(n=48, h=64, w=64, n_hyp=128, n_samp=10, outlier_frac=0.4)),
+    ('sparse', dict(n=128, h=24, w=28, n_hyp=100, n_samp=10, mask_fill=0.3)),
+    ('tiny3', dict(n=256, h=12, w=12, n_hyp=32, n_samp=3, mask_fill=0.3, border=0)),
+    ('tiny16', dict(n=128, h=16, w=20, n_hyp=64, n_samp=16, mask_fill=0.1, border=0)),
+    ('large', dict(n=12, h=112, w=112, n_hyp=128, n_samp=10)),
+]
+
+
+@pytest.mark.parametrize('name,cfg', SCREEN_REGIMES, ids=[r[0] for r in SCREEN_REGIMES])
+def test_screen_interval_contains_double_residual(lib, name, cfg):
+    import importlib
+    import zlib
+    synth = importlib.import_module('3d_mot_differentiable_pose_estimation_b200.synth')
+    cfg = dict(cfg)
+    n_obj, h, w = cfg.pop('n'), cfg.pop('h'), cfg.pop('w')
+    d = synth.make_objects(n_obj, h, w, seed=zlib.crc32(name.encode()) % 10000 + 7, **cfg)
+    noc, depth, mask = d['noc'].numpy(), d['depth'].numpy(), d['mask'].numpy()
+    xy0, idx = d['bbox_xy0'].numpy(), d['sample_idx'].numpy()
+    kinv = np.linalg.inv(po.motfront_intrinsics())
+    kinv4 = np.array([kinv[0, 0], kinv[0, 2], kinv[1, 1], kinv[1, 2]])
+    n_hyp, n_samp = idx.shape[1], idx.shape[2]
+    ip = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_int))
+    fp = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+    n_fin = n_cand = n_objs = 0
+    worst = 0.0
+    for i in range(n_obj):
+        rows, cols = np.where((mask[i] != 0) & (depth[i] > 0))
+        n = rows.size
+        if n == 0:
+            continue
+        pts_noc = np.ascontiguousarray(noc[i][:, rows, cols].T, dtype=np.float32)
+        z = np.ascontiguousarray(depth[i][rows, cols], dtype=np.float32)
+        fr = np.ascontiguousarray(rows + xy0[i, 1], dtype=np.int32)
+        fc = np.ascontiguousarray(cols + xy0[i, 0], dtype=np.int32)
+        id_ = np.ascontiguousarray(idx[i], dtype=np.int32)
+        r64, lo, hi = np.zeros(n_hyp), np.zeros(n_hyp), np.zeros(n_hyp)
+        lib.pf_check_screen(fp(pts_noc), fp(z), ip(fr), ip(fc), ctypes.c_int(n), _dp(kinv4), ip(id_),
+                            ctypes.c_int(n_hyp), ctypes.c_int(n_samp), ctypes.c_int(1), _dp(r64), _dp(lo), _dp(hi))
+        fin = np.isfinite(lo) & np.isfinite(hi) & np.isfinite(r64)
+        assert np.all(lo[fin] <= r64[fin]) and np.all(r64[fin] <= hi[fin]), (name, i)
+        half = 0.5 * (hi[fin] - lo[fin])
+        if fin.any():
+            worst = max(worst, float(np.max(np.abs(r64[fin] - 0.5 * (hi[fin] + lo[fin])) / np.maximum(half, 1e-300))))
+        # candidate rule of the kernel: keeps the first minimum (and every hypothesis below the stop threshold)
+        u = np.min(np.where(np.isnan(hi), np.inf, hi))
+        cand = ~(lo > u)
+        if np.isfinite(r64).any():
+            win = int(np.nanargmin(r64))
+            assert cand[win], (name, i, win)
+        n_fin += int(fin.sum())
+        n_cand += int(cand.sum())
+        n_objs += 1
+    assert n_objs > 0
+    print(f'screen[{name}]: {n_objs} objects, {n_fin} finite intervals, worst |error| / half-width = {worst:.3g}, '
+          f'candidates per object = {n_cand / n_objs:.2f}')
+    assert worst < 0.5          # the interval is at least twice as wide as any error seen
