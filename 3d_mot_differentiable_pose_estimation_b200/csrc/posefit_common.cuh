@@ -72,6 +72,7 @@ struct FwdParams {
   int32_t* n_valid;
   uint8_t* inlier_mask;
   int32_t* winner;
+  int32_t* redo_flag;           // RANSAC: set by fit_ransac_crop_kernel when fit_ransac_kernel has to do the batch (skewed K)
   double ratio_adapt;
   double pass_override, stop_override;   // > 0: use instead of the data-derived PassT / StopT (getRANSACInliers' arguments)
   int kinv_per_object;
@@ -94,6 +95,7 @@ struct FwdParams {
   int chunks_per_obj, chunks_per_warp, max_parts, vec_ok;
   uint32_t warp_smem_bytes;     // per-warp shared memory: cp.async ring + ray tables
   // shared-memory carve-up (bytes from the dynamic smem base)
+  uint32_t off_ftab;            // RANSAC SCREEN variant: float ray tables (rx[W], ry[H]), 16-byte aligned
   uint32_t off_geom, off_tables, off_red, off_bits, off_prefix, off_stats, off_res, off_tf, off_stages;
   uint32_t stage_bytes, st_depth, st_mask, st_idx;   // offsets inside one stage
 };

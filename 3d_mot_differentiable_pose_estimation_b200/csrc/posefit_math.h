@@ -292,12 +292,23 @@ PF_NOINLINE Mat3 rotation_redo(Mat3 C, Mat3 Cn) {
 // BEFORE a step bounds the error after it by its square; if it has not collapsed before the
 // second step the solve is redone from a double-precision Jacobi start (near-degenerate C only).
 // EXTRA_STEP adds a third Newton step (used for the once-per-object fits; hypotheses skip it).
+// `start` (optional): a rotation within ~1e-5 of the solution (the float fit of the RANSAC screen); the Jacobi start is
+// skipped, everything else -- orthonormalisation, Newton steps, the convergence test with its double-precision redo --
+// is unchanged, so the result is the same fixed point.
 template <bool EXTRA_STEP, bool WANT_LINV>
-PF_HD void solve_rotation(const double* C, double* R, double* H, double* Linv) {
+PF_HD void solve_rotation(const double* C, double* R, double* H, double* Linv, const float* start = nullptr,
+                          bool use_start = false) {
   double m = 0.0;
 #pragma unroll
   for (int i = 0; i < 9; ++i) m = fmax(m, fabs(C[i]));
-  const bool nonzero = rotation_start<float, 3>(C, R);
+  bool nonzero;
+  if (use_start) {
+    nonzero = (m > 0.0) && (m < 1e300);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) R[i] = nonzero ? (double)start[i] : ((i % 4 == 0) ? 1.0 : 0.0);
+  } else {
+    nonzero = rotation_start<float, 3>(C, R);
+  }
 #pragma unroll
   for (int i = 0; i < 6; ++i) { H[i] = 0.0; if (WANT_LINV) Linv[i] = 0.0; }
   if (!nonzero) return;
@@ -347,7 +358,8 @@ PF_HD void solve_rotation(const double* C, double* R, double* H, double* Linv) {
 // ox / oy (optional): origin the sums were shifted by (x - ox, y - oy were accumulated); C and
 // var are shift invariant, the means are restored before t is formed.
 template <bool PRECISE>
-PF_HD void fit_from_moments(const Moments& mo, Fit& f, const double* ox = nullptr, const double* oy = nullptr) {
+PF_HD void fit_from_moments(const Moments& mo, Fit& f, const double* ox = nullptr, const double* oy = nullptr,
+                            const float* start = nullptr, bool use_start = false) {
   f.n = mo.n;
   f.s = 1.0;
 #pragma unroll
@@ -379,7 +391,7 @@ PF_HD void fit_from_moments(const Moments& mo, Fit& f, const double* ox = nullpt
     for (int i = 0; i < 9; ++i) C[i] = 0.0;
     f.var = 0.0;
   }
-  solve_rotation<PRECISE, PRECISE>(C, f.R, f.H, f.Linv);   // hypotheses never need Linv
+  solve_rotation<PRECISE, PRECISE>(C, f.R, f.H, f.Linv, start, use_start);   // hypotheses never need Linv
   if (ox != nullptr) {
 #pragma unroll
     for (int i = 0; i < 3; ++i) { f.mux[i] += ox[i]; f.muy[i] += oy[i]; }
@@ -449,13 +461,23 @@ struct ScreenFit {
   float A[9];      // scoring transform (s * R^T when ref_compat, else s * R), row-major
   float t[3];
   float s;
+  float R[9];      // the float rotation (true R), start of the double polish of a candidate
   float mx[3], my[3];   // sample means (unshifted)
+  float q;         // max |R^T R - I|: the float rotation's distance from orthogonality
   float rho;       // relative error estimate of A and t's rotation part; +inf = not usable
 };
 
 constexpr float kScreenEps = 1.1920929e-7f;       // 2^-23
 
-// sums are over x - ox, y - oy (ox, oy = first sample), n = number of samples (the first included)
+// sums are over x - ox, y - oy (ox, oy = first sample), n = number of samples (the first included).
+// Rotation: Markley's FOAM closed form instead of a Jacobi sweep (about a quarter of the instructions, no dependent
+// chain of nine pair rotations): with B = C / |C|_F, the largest root lambda of
+//   psi(l) = (l^2 - 1)^2 - 8 l det B - 4 |adj B|_F^2          (roots: +-s1 +-s2 +-s3, even number of minus signs)
+// found by Newton from sqrt(3) >= lambda (monotone from above), gives the maximiser of tr(R^T C) over SO(3) as
+//   R = [ (kappa + 1) B + lambda adj(B)^T - B B^T B ] / zeta,  kappa = (lambda^2 - 1) / 2,  zeta = kappa lambda - det B,
+// where zeta = (s1+s2)(s1+s3)(s2+s3) = det L, so 4 zeta / (lambda + 1)^2 bounds the smallest eigenvalue of L
+// from below.  Whatever the float arithmetic loses (small zeta) shows up in the checks that
+// follow -- Newton residual of R, its distance from orthogonality -- and widens the interval.
 PF_HD void screen_fit32(int n, const float* sx, const float* sy, const float* syx, float sxx, float syy,
                         const float* ox, const float* oy, bool ref_compat, ScreenFit& f) {
   const float inf = __builtin_huge_valf();
@@ -472,71 +494,132 @@ PF_HD void screen_fit32(int n, const float* sx, const float* sy, const float* sy
   const float mag = pf_sqrt(ex * ey);               // >= every |syx| * rn (Cauchy-Schwarz)
 #pragma unroll
   for (int i = 0; i < 3; ++i) { f.mx[i] = mux[i] + ox[i]; f.my[i] = muy[i] + oy[i]; }
-  float m = 0.0f;
+  float nf2 = 0.0f;
 #pragma unroll
-  for (int i = 0; i < 9; ++i) m = fmaxf(m, pf_abs(C[i]));
+  for (int i = 0; i < 9; ++i) nf2 = fmaf(C[i], C[i], nf2);
   f.rho = inf;
+  f.q = 0.0f;
   f.s = 1.0f;
 #pragma unroll
-  for (int i = 0; i < 9; ++i) f.A[i] = (i % 4 == 0) ? 1.0f : 0.0f;
+  for (int i = 0; i < 9; ++i) { f.A[i] = (i % 4 == 0) ? 1.0f : 0.0f; f.R[i] = f.A[i]; }
 #pragma unroll
   for (int i = 0; i < 3; ++i) f.t[i] = f.my[i] - f.mx[i];
-  if (!(m > 1e-5f * mag) || !(mag < 1e30f) || !(var > 0.0f)) return;     // degenerate / non-finite: double decides
-  const float inv = 1.0f / m;
-  float a0[3], a1[3], a2[3], v0[3] = {1, 0, 0}, v1[3] = {0, 1, 0}, v2[3] = {0, 0, 1};
+  if (!(nf2 > 1e-10f * mag * mag) || !(mag < 1e18f) || !(var > 0.0f)) return;   // degenerate / non-finite: double decides
+  const float inv = pf_rsqrt(nf2);                  // 1 / |C|_F
+  float B[9];
 #pragma unroll
-  for (int i = 0; i < 3; ++i) { a0[i] = C[3 * i] * inv; a1[i] = C[3 * i + 1] * inv; a2[i] = C[3 * i + 2] * inv; }
+  for (int i = 0; i < 9; ++i) B[i] = C[i] * inv;
+  // adjugate transposed (= cofactor matrix): cof[3 i + j] = cofactor of B[i][j]
+  float cof[9];
+  cof[0] = B[4] * B[8] - B[5] * B[7]; cof[1] = B[5] * B[6] - B[3] * B[8]; cof[2] = B[3] * B[7] - B[4] * B[6];
+  cof[3] = B[2] * B[7] - B[1] * B[8]; cof[4] = B[0] * B[8] - B[2] * B[6]; cof[5] = B[1] * B[6] - B[0] * B[7];
+  cof[6] = B[1] * B[5] - B[2] * B[4]; cof[7] = B[2] * B[3] - B[0] * B[5]; cof[8] = B[0] * B[4] - B[1] * B[3];
+  const float det = B[0] * cof[0] + B[1] * cof[1] + B[2] * cof[2];
+  float c4 = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) c4 = fmaf(cof[i], cof[i], c4);
+  c4 *= 4.0f;
+  const float b8 = 8.0f * det;
+  float lam = 1.7320508f, step = 1.0f;
 #pragma unroll 1
-  for (int sweep = 0; sweep < 3; ++sweep) {
-    jacobi_pair(a0, a1, v0, v1);
-    jacobi_pair(a0, a2, v0, v2);
-    jacobi_pair(a1, a2, v1, v2);
+  for (int it = 0; it < 24 && step > 2e-7f * lam; ++it) {   // Newton on the quartic, from above (5-6 steps; a near-double
+    const float t = fmaf(lam, lam, -1.0f);                   //  root -- s2 + s3 small -- converges linearly and takes more)
+    const float psi = fmaf(t, t, -fmaf(b8, lam, c4));
+    const float dpsi = fmaf(4.0f * lam, t, -b8);
+    step = pf_div(psi, dpsi);
+    lam -= step;
   }
-  float n0 = a0[0] * a0[0] + a0[1] * a0[1] + a0[2] * a0[2];
-  float n1 = a1[0] * a1[0] + a1[1] * a1[1] + a1[2] * a1[2];
-  float n2 = a2[0] * a2[0] + a2[1] * a2[1] + a2[2] * a2[2];
-  if (n0 < n1) { swap_cols(a0, a1); swap_cols(v0, v1); const float t = n0; n0 = n1; n1 = t; }
-  if (n0 < n2) { swap_cols(a0, a2); swap_cols(v0, v2); const float t = n0; n0 = n2; n2 = t; }
-  if (n1 < n2) { swap_cols(a1, a2); swap_cols(v1, v2); const float t = n1; n1 = n2; n2 = t; }
-  float u0[3], u1[3], u2[3], w2[3];
-  const float r0 = pf_rsqrt(n0);
-#pragma unroll
-  for (int i = 0; i < 3; ++i) u0[i] = a0[i] * r0;
-  const float d = u0[0] * a1[0] + u0[1] * a1[1] + u0[2] * a1[2];
-#pragma unroll
-  for (int i = 0; i < 3; ++i) u1[i] = a1[i] - d * u0[i];
-  const float l1 = u1[0] * u1[0] + u1[1] * u1[1] + u1[2] * u1[2];
-  if (!(l1 > 1e-6f * n0)) return;                   // (numerically) rank one: the rotation is not determined
-  const float r1 = pf_rsqrt(l1);
-#pragma unroll
-  for (int i = 0; i < 3; ++i) u1[i] *= r1;
-  cross3(u0, u1, u2);
-  cross3(v0, v1, w2);
-  // signed third singular value u2^T C w2 = det(V) (u2 . C v2) and the smallest eigenvalue of L: sigma2 + sigma3
-  const float dv = w2[0] * v2[0] + w2[1] * v2[1] + w2[2] * v2[2];
-  const float s3 = (u2[0] * a2[0] + u2[1] * a2[1] + u2[2] * a2[2]) * dv;
-  const float s1 = n0 * r0, s2 = l1 * r1;
-  const float gap = s2 + s3;
-  if (!(gap > 3e-3f * s1)) return;                  // ill-conditioned rotation: double decides
+  const float kappa = 0.5f * fmaf(lam, lam, -1.0f);
+  const float zeta = fmaf(kappa, lam, -det);
+  if (!(zeta > 1e-5f) || !(lam > 0.0f)) return;     // ill-conditioned rotation (or NaN): double decides
+  // G = B^T B (symmetric), P = B G
+  float G[6];
+  G[0] = B[0] * B[0] + B[3] * B[3] + B[6] * B[6]; G[1] = B[0] * B[1] + B[3] * B[4] + B[6] * B[7];
+  G[2] = B[0] * B[2] + B[3] * B[5] + B[6] * B[8]; G[3] = B[1] * B[1] + B[4] * B[4] + B[7] * B[7];
+  G[4] = B[1] * B[2] + B[4] * B[5] + B[7] * B[8]; G[5] = B[2] * B[2] + B[5] * B[5] + B[8] * B[8];
+  const float rz = 1.0f / zeta, k1 = kappa + 1.0f;
   float R[9];
 #pragma unroll
-  for (int i = 0; i < 3; ++i)
+  for (int i = 0; i < 3; ++i) {
+    const float b0 = B[3 * i], b1 = B[3 * i + 1], b2 = B[3 * i + 2];
+    R[3 * i] = (k1 * b0 + lam * cof[3 * i] - (b0 * G[0] + b1 * G[1] + b2 * G[2])) * rz;
+    R[3 * i + 1] = (k1 * b1 + lam * cof[3 * i + 1] - (b0 * G[1] + b1 * G[3] + b2 * G[4])) * rz;
+    R[3 * i + 2] = (k1 * b2 + lam * cof[3 * i + 2] - (b0 * G[2] + b1 * G[4] + b2 * G[5])) * rz;
+  }
+  // Newton-Schulz towards O(3), then one float Newton step on SO(3) (the very step newton_step takes in double): FOAM
+  // loses digits where zeta is small, the two steps give them back as far as float can hold them
+  {
+    float Gm[9], N[9];
 #pragma unroll
-    for (int j = 0; j < 3; ++j) R[3 * i + j] = u0[i] * v0[j] + u1[i] * v1[j] + u2[i] * w2[j];
-  // M = R^T Cn: trace -> scale, skew part -> Newton residual of this start
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j)
+        Gm[3 * i + j] = -0.5f * (R[i] * R[j] + R[3 + i] * R[3 + j] + R[6 + i] * R[6 + j]) + (i == j ? 1.5f : 0.0f);
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) N[3 * i + j] = R[3 * i] * Gm[j] + R[3 * i + 1] * Gm[3 + j] + R[3 * i + 2] * Gm[6 + j];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) R[i] = N[i];
+  }
   float M[9];
+  {
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) M[3 * i + j] = R[i] * B[j] + R[3 + i] * B[3 + j] + R[6 + i] * B[6 + j];
+    const float h01 = 0.5f * (M[1] + M[3]), h02 = 0.5f * (M[2] + M[6]), h12 = 0.5f * (M[5] + M[7]);
+    const float tr = M[0] + M[4] + M[8];
+    const float l00 = tr - M[0], l11 = tr - M[4], l22 = tr - M[8], l01 = -h01, l02 = -h02, l12 = -h12;
+    const float c00 = l11 * l22 - l12 * l12, c01 = l02 * l12 - l01 * l22, c02 = l01 * l12 - l02 * l11;
+    const float dl = l00 * c00 + l01 * c01 + l02 * c02;
+    const float k0 = M[7] - M[5], k1s = M[2] - M[6], k2 = M[3] - M[1];
+    if (dl > 1e-6f) {
+      const float rd = 1.0f / dl;
+      const float c11 = l00 * l22 - l02 * l02, c12 = l01 * l02 - l00 * l12, c22 = l00 * l11 - l01 * l01;
+      const float w0 = (c00 * k0 + c01 * k1s + c02 * k2) * rd;
+      const float w1 = (c01 * k0 + c11 * k1s + c12 * k2) * rd;
+      const float w2 = (c02 * k0 + c12 * k1s + c22 * k2) * rd;
+      const float th2 = w0 * w0 + w1 * w1 + w2 * w2;
+      if (th2 < 0.01f) {                            // a correction, not a rescue
+        const float a = 1.0f - th2 * (1.0f / 6.0f), b = 0.5f - th2 * (1.0f / 24.0f);
+        float E[9];
+        E[0] = 1.0f + b * (w0 * w0 - th2); E[1] = -a * w2 + b * w0 * w1;      E[2] = a * w1 + b * w0 * w2;
+        E[3] = a * w2 + b * w0 * w1;      E[4] = 1.0f + b * (w1 * w1 - th2); E[5] = -a * w0 + b * w1 * w2;
+        E[6] = -a * w1 + b * w0 * w2;     E[7] = a * w0 + b * w1 * w2;      E[8] = 1.0f + b * (w2 * w2 - th2);
+        float N[9];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+          for (int j = 0; j < 3; ++j) N[3 * i + j] = R[3 * i] * E[j] + R[3 * i + 1] * E[3 + j] + R[3 * i + 2] * E[6 + j];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) R[i] = N[i];
+      }
+    }
+  }
+  // checks: M = R^T B (trace -> scale, skew part -> Newton residual of R), Q = R^T R - I (distance from O(3))
 #pragma unroll
   for (int i = 0; i < 3; ++i)
 #pragma unroll
-    for (int j = 0; j < 3; ++j)
-      M[3 * i + j] = R[i] * (C[j] * inv) + R[3 + i] * (C[3 + j] * inv) + R[6 + i] * (C[6 + j] * inv);
+    for (int j = 0; j < 3; ++j) M[3 * i + j] = R[i] * B[j] + R[3 + i] * B[3 + j] + R[6 + i] * B[6 + j];
   const float trh = M[0] + M[4] + M[8];
   const float kn = fmaxf(pf_abs(M[7] - M[5]), fmaxf(pf_abs(M[2] - M[6]), pf_abs(M[3] - M[1])));
-  if (!(trh > 0.0f)) return;
-  const float dc = 8.0f * kScreenEps * mag * inv;  // rounding of the (normalised) covariance entries
-  const float s = trh * m / var;                    // pose_utils.py:47-50 (var * trh != 0 here)
-  f.rho = (kn + dc) / gap + 3.0f * dc / trh + 8.0f * kScreenEps * ex / var;
+  float q = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = i; j < 3; ++j)
+      q = fmaxf(q, pf_abs(R[i] * R[j] + R[3 + i] * R[3 + j] + R[6 + i] * R[6 + j] - (i == j ? 1.0f : 0.0f)));
+  if (!(trh > 0.0f) || !(q < 1e-2f)) return;
+  const float dc = 8.0f * kScreenEps * mag * inv;   // rounding of the (normalised) covariance entries
+  const float s = trh / (inv * var);                // pose_utils.py:47-50: tr(R^T C) / var
+  // smallest eigenvalue of L: s2 + s3 = zeta / ((s1+s2)(s1+s3)) and (s1+s2)(s1+s3) <= ((lambda + s1) / 2)^2 <= ((lambda + 1) / 2)^2
+  const float gap = 4.0f * zeta / ((lam + 1.0f) * (lam + 1.0f));
+  f.rho = (kn + dc) / gap + 2.0f * q + 3.0f * dc / trh + 8.0f * kScreenEps * ex / var;
   f.s = s;
+  f.q = q;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) f.R[i] = R[i];
 #pragma unroll
   for (int i = 0; i < 3; ++i)
 #pragma unroll
@@ -550,14 +633,33 @@ PF_HD void screen_fit32(int n, const float* sx, const float* sy, const float* sy
 // contains the residual^2 of the double fit: |d r2| <= 2 sqrt(r2) (|dA| sqrt(sum |x|^2) + |dt| sqrt(n)) to first
 // order; x_rms = sqrt(sum_i |x_i|^2 / n) over ALL correspondences.  The leading factor 2 is a safety margin on top of the
 // worst-case rounding constants (tests/test_math_host.py: no error above 5 % of the half-width on any regime).
-PF_HD double screen_interval(const ScreenFit& f, double r2, double n_all, double x_rms) {
+PF_HD double screen_interval(const ScreenFit& f, double r2, double n_all, double x_rms, double tr_sxx = 0.0) {
   if (!(f.rho < 1e30f) || !(r2 >= 0.0) || !(r2 < 1e300)) return __builtin_huge_val();
   const double s = (double)pf_abs(f.s), rho = (double)f.rho;
   const double amx = (double)(pf_abs(f.mx[0]) + pf_abs(f.mx[1]) + pf_abs(f.mx[2]));
   const double amy = (double)(pf_abs(f.my[0]) + pf_abs(f.my[1]) + pf_abs(f.my[2]));
   const double e8 = 8.0 * (double)kScreenEps;
   const double lin = s * rho * (x_rms + amx) + e8 * (amy + s * amx);
-  return 2.0 * (2.0 * sqrt(r2 * n_all) * lin + n_all * lin * lin);
+  // tr_sxx > 0: r2 came from residual_sq_iso, whose quadratic term assumes an exactly orthogonal rotation
+  return 2.0 * (2.0 * sqrt(r2 * n_all) * lin + n_all * lin * lin) + 3.0 * (double)f.q * s * s * tr_sxx;
+}
+
+// The same closed form for a SCALED ROTATION A = s Q (Q orthogonal): <A Sxx, A> = s^2 tr(Sxx), so only the trace of
+// the centred source scatter is needed (the crop kernel accumulates 18 sums per pixel instead of 23).  For a Q that is
+// orthogonal only up to q = max |Q^T Q - I| the quadratic term is off by at most 3 q s^2 tr(Sxx): callers add that to
+// their interval (the double fits end in a Newton-Schulz step: q ~ 1e-16).
+PF_HD double residual_sq_iso(double n, const double* mux, const double* muy, double Syy, const double* Syx,
+                             double trSxx, const double* A, const double* t, double s) {
+  double lin = 0.0;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) lin = fma(A[i], Syx[i], lin);
+  double dd = 0.0;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const double d = muy[i] - (A[3 * i] * mux[0] + A[3 * i + 1] * mux[1] + A[3 * i + 2] * mux[2]) - t[i];
+    dd = fma(d, d, dd);
+  }
+  return fma(n, dd, fma(s * s, trSxx, fma(-2.0, lin, Syy)));
 }
 
 // Scoring transform of a fit.  ref_compat: A = s * R^T, the block the reference really builds

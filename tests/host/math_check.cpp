@@ -158,8 +158,10 @@ void pf_check_screen(const float* noc, const float* z, const int* rows, const in
     double Ad[9], td[3];
     for (int i = 0; i < 9; ++i) Ad[i] = sf.A[i];
     for (int i = 0; i < 3; ++i) td[i] = sf.t[i];
-    const double r2 = residual_sq(g, Ad, td);
-    const double e = screen_interval(sf, r2, (double)n, x_rms);
+    // as the crop kernel evaluates it: isotropic closed form (+ its orthogonality allowance in the interval)
+    const double tr = g.Sxx[0] + g.Sxx[3] + g.Sxx[5];
+    const double r2 = residual_sq_iso(g.n, g.mux, g.muy, g.Syy, g.Syx, tr, Ad, td, (double)sf.s);
+    const double e = screen_interval(sf, r2, (double)n, x_rms, tr);
     lo[h] = r2 - e;
     hi[h] = r2 + e;
   }

@@ -316,8 +316,15 @@ def test_tma_and_fallback_loaders_agree(pf, knob):
     b_ = pf.pose_fit_raw(t['noc'], t['depth'], t['mask'], t['bbox_xy0'])
     br = pf.pose_fit_raw(t['noc'], t['depth'], t['mask'], t['bbox_xy0'], sample_idx=t['sample_idx'])
     torch.cuda.synchronize()
-    assert torch.equal(a.pose, b_.pose) and torch.equal(ar.pose, br.pose)
-    assert torch.equal(ar.inlier_mask, br.inlier_mask)
+    # (RANSAC: NO_TMA selects the general kernel, the default the crop kernel -- same masks, poses to rounding)
+    assert torch.equal(a.pose, b_.pose) and float((ar.pose[:, :15] - br.pose[:, :15]).abs().max()) < 1e-9
+    assert torch.equal(ar.inlier_mask, br.inlier_mask) and torch.equal(ar.winner, br.winner)
+    knob.set('POSEFIT_RANSAC_SCREEN', '0')
+    cr = pf.pose_fit_raw(t['noc'], t['depth'], t['mask'], t['bbox_xy0'], sample_idx=t['sample_idx'])
+    knob.clear('POSEFIT_NO_TMA')
+    dr = pf.pose_fit_raw(t['noc'], t['depth'], t['mask'], t['bbox_xy0'], sample_idx=t['sample_idx'])
+    torch.cuda.synchronize()
+    assert torch.equal(cr.pose, dr.pose) and torch.equal(cr.inlier_mask, dr.inlier_mask)
 
 
 def test_launch_variants_agree(pf, knob):
@@ -344,7 +351,10 @@ def test_launch_variants_agree(pf, knob):
                 {'POSEFIT_SMALL_WARPS': '16', 'POSEFIT_PAIR': '1'}, {'POSEFIT_NO_IDX_PRELOAD': '1'},
                 {'POSEFIT_NO_EARLY_ISSUE': '1'}, {'POSEFIT_RANSAC_SCREEN': '0'}, {'POSEFIT_NO_SCREEN': '1'},
                 {'POSEFIT_RANSAC_THREADS': '160'}, {'POSEFIT_RANSAC_THREADS': '192'},
-                {'POSEFIT_RANSAC_SCREEN': '0', 'POSEFIT_RANSAC_THREADS': '256'}]
+                {'POSEFIT_RANSAC_THREADS': '256'}, {'POSEFIT_RANSAC_SCREEN': '0', 'POSEFIT_RANSAC_THREADS': '256'},
+                {'POSEFIT_RANSAC_SCREEN': '0', 'POSEFIT_RANSAC_THREADS': '256', 'POSEFIT_RANSAC_MINB': '3'},
+                {'POSEFIT_RANSAC_SCREEN': '0', 'POSEFIT_NO_IDX_PRELOAD': '1'},
+                {'POSEFIT_RANSAC_SCREEN': '0', 'POSEFIT_NO_EARLY_ISSUE': '1'}]
     for env in variants:
         for k, v in env.items():
             knob.set(k, v)
@@ -369,6 +379,57 @@ def test_ransac_fast_and_generic_passes_agree(pf, knob):
     assert torch.equal(a.status, b.status)
     assert float((a.pose[:, :13] - b.pose[:, :13]).abs().max()) < 1e-10
     assert float((a.pose[:, 15] - b.pose[:, 15]).abs().max() / b.pose[:, 15].abs().max()) < 1e-6
+
+
+def test_crop_kernel_matches_general_kernel(pf, knob):
+    """fit_ransac_crop_kernel (float screen of the hypotheses, double fit of the candidates / of the winner when a pixel
+    lands in the guard band) against fit_ransac_kernel (every hypothesis fitted in double): inlier masks, winners and
+    statuses bit-identical, poses to rounding -- on benchmark-like, clean (many near-ties), noise-free (EVERY hypothesis
+    a candidate), heavily contaminated, sparse and early-stopping data, with 3 / 10 / 16 samples, for every CTA size;
+    and a skewed K^-1, which the crop kernel hands back to the general kernel through its flag."""
+    cases = [dict(b=1500, h=64, w=64, n_hyp=128, n_samp=10, seed=70),     # several objects per CTA
+             dict(b=64, h=64, w=64, n_hyp=128, n_samp=10, seed=71),
+             dict(b=32, h=64, w=64, n_hyp=128, n_samp=10, seed=72, outlier_frac=0.0),
+             dict(b=16, h=64, w=64, n_hyp=64, n_samp=10, seed=73, outlier_frac=0.0, noc_noise=0.0),
+             dict(b=32, h=64, w=64, n_hyp=100, n_samp=10, seed=74, outlier_frac=0.4),
+             dict(b=32, h=48, w=64, n_hyp=128, n_samp=16, seed=75, mask_fill=0.3),
+             dict(b=32, h=32, w=32, n_hyp=32, n_samp=3, seed=76, mask_fill=0.1, border=0),
+             dict(b=6, h=112, w=112, n_hyp=128, n_samp=10, seed=77),
+             dict(b=24, h=40, w=52, n_hyp=200, n_samp=10, seed=78),
+             dict(b=16, h=64, w=64, n_hyp=1, n_samp=10, seed=79)]
+    for cfg in cases:
+        cfg = dict(cfg)
+        b, h, w, seed = cfg.pop('b'), cfg.pop('h'), cfg.pop('w'), cfg.pop('seed')
+        d = pf.synth.make_objects(b, h, w, seed=seed, **cfg)
+        t = _cuda(d)
+        knob.set('POSEFIT_RANSAC_SCREEN', '0')
+        ref = pf.pose_fit_raw(t['noc'], t['depth'], t['mask'], t['bbox_xy0'], sample_idx=t['sample_idx'])
+        torch.cuda.synchronize()
+        knob.clear('POSEFIT_RANSAC_SCREEN')
+        for nt in ('128', '160', '192', '256'):
+            knob.set('POSEFIT_RANSAC_THREADS', nt)
+            out = pf.pose_fit_raw(t['noc'], t['depth'], t['mask'], t['bbox_xy0'], sample_idx=t['sample_idx'])
+            torch.cuda.synchronize()
+            knob.clear('POSEFIT_RANSAC_THREADS')
+            assert torch.equal(out.status, ref.status), (cfg, nt)
+            assert torch.equal(out.n_valid, ref.n_valid), (cfg, nt)
+            assert torch.equal(out.winner, ref.winner), (cfg, nt)
+            assert torch.equal(out.inlier_mask, ref.inlier_mask), (cfg, nt)
+            assert float((out.pose[:, :15] - ref.pose[:, :15]).abs().max()) < 1e-9, (cfg, nt)
+            assert float(((out.pose[:, 15] - ref.pose[:, 15]) / ref.pose[:, 15].clamp_min(1e-30)).abs().max()) < 1e-6
+    # planted exact similarity: the early stop (pose_utils.py:80-81) fires in both kernels at the same hypothesis
+    d = pf.synth.make_objects(8, 64, 64, seed=80, n_hyp=64, outlier_frac=0.0, noc_noise=0.0)
+    t = _cuda(d)
+    # skewed intrinsics: not a pinhole -> the crop kernel declines, the general kernel does the batch
+    k = torch.linalg.inv(pf.synth.motfront_intrinsics() + torch.tensor([[0, 3.5, 0], [0, 0, 0], [0, 0, 0.]])).cuda()
+    knob.set('POSEFIT_RANSAC_SCREEN', '0')
+    ref = pf.pose_fit_raw(t['noc'], t['depth'], t['mask'], t['bbox_xy0'], k, sample_idx=t['sample_idx'])
+    torch.cuda.synchronize()
+    knob.clear('POSEFIT_RANSAC_SCREEN')
+    out = pf.pose_fit_raw(t['noc'], t['depth'], t['mask'], t['bbox_xy0'], k, sample_idx=t['sample_idx'])
+    torch.cuda.synchronize()
+    assert torch.equal(out.inlier_mask, ref.inlier_mask) and torch.equal(out.winner, ref.winner)
+    assert torch.equal(out.pose, ref.pose)
 
 
 def test_edge_cases(pf):
