@@ -27,7 +27,7 @@ SYMBOLS = ('posefit_version', 'posefit_error_string', 'posefit_workspace_bytes',
            'posefit_points_evaluate', 'posefit_transform_points', 'posefit_epilogue', 'posefit_clip_mask', 'posefit_sor_mask',
            'posefit_sor_workspace_bytes', 'posefit_resample_noc', 'posefit_resample_noc_backward',
            'posefit_gather_crops', 'posefit_edge_features', 'posefit_edge_workspace_bytes',
-           'posefit_debug_reload_env')
+           'posefit_debug_reload_env', 'posefit_forward_ex', 'posefit_forward_ransac_ex')
 
 _lock = threading.Lock()
 _lib = None
@@ -72,6 +72,11 @@ def _declare(lib):
     lib.posefit_forward_ransac.restype = i32
     lib.posefit_forward_ransac.argtypes = [vp, vp, vp, vp, vp, i32, vp, i32, i32, i32, i32, i32, f64, i32,
                                            vp, vp, vp, vp, vp, vp, vp, sz, vp]
+    lib.posefit_forward_ex.restype = i32
+    lib.posefit_forward_ex.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]
+    lib.posefit_forward_ransac_ex.restype = i32
+    lib.posefit_forward_ransac_ex.argtypes = [vp, vp, vp, vp, vp, i32, vp, i32, i32, i32, i32, i32, f64, i32,
+                                              vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]
     lib.posefit_backward.restype = i32
     lib.posefit_backward.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]
     lib.posefit_backward_workspace_bytes.restype = sz

@@ -298,6 +298,9 @@ __global__ void __launch_bounds__(512, 1) fit_moments_kernel(const FwdParams p) 
           ok[j] = (m4 & (0xffu << (8 * j))) != 0u && zz[j] > 0.0f;
           any = any || ok[j];
         }
+        if (p.valid_mask != nullptr)
+          *reinterpret_cast<uint32_t*>(p.valid_mask + (size_t)obj * P + px0 + u * kChunkPx) =
+              (ok[0] ? 1u : 0u) | (ok[1] ? 0x100u : 0u) | (ok[2] ? 0x10000u : 0u) | (ok[3] ? 0x1000000u : 0u);
         if (__any_sync(0xffffffffu, any)) {
           const float4 a4 = *reinterpret_cast<const float4*>(st);
           const float4 b4 = *reinterpret_cast<const float4*>(st + 512);
@@ -406,6 +409,17 @@ __global__ void __launch_bounds__(512, 1) fit_moments_kernel(const FwdParams p) 
       for (int j = 0; j < 4; ++j) {                           // pose_estimation.py:23-25
         ok[j] = (m4 & (0xffu << (8 * j))) != 0u && zz[j] > 0.0f && (VEC != 0 || px0 + j < P);
         any = any || ok[j];
+      }
+      if (p.valid_mask != nullptr && in_obj) {
+        uint8_t* vm = p.valid_mask + (size_t)obj * P + px0;
+        if (VEC != 0) {
+          *reinterpret_cast<uint32_t*>(vm) =
+              (ok[0] ? 1u : 0u) | (ok[1] ? 0x100u : 0u) | (ok[2] ? 0x10000u : 0u) | (ok[3] ? 0x1000000u : 0u);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (px0 + j < P) vm[j] = ok[j] ? 1 : 0;
+        }
       }
       if (__any_sync(0xffffffffu, any)) {
         const float4 a4 = *reinterpret_cast<const float4*>(st);

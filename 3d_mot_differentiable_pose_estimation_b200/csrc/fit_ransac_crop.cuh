@@ -48,9 +48,16 @@ struct CropShared {                 // lives at off_stats
 };
 
 // ---- pass 1: validity bitmap + 18 raw sums (a = noc, z instead of y2 = -z, see LaneSums) + the two norm sums ---------
+__device__ __forceinline__ float sqrt_approx(float x) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
 template <int NT>
 __device__ __forceinline__ void crop_pass1(const FwdParams& p, const unsigned char* stage, const double* rxc,
-                                           const double* ryr, uint32_t* bits, int tid, double (&raw)[kCropAcc]) {
+                                           const double* ryr, const float* cwf, const float* rwf, uint32_t* bits, int tid,
+                                           double (&raw)[kCropAcc]) {
   const int P = p.P, lane = tid & 31;
   const float* snoc = reinterpret_cast<const float*>(stage);
   const float* sdep = reinterpret_cast<const float*>(stage + p.st_depth);
@@ -100,6 +107,9 @@ __device__ __forceinline__ void crop_pass1(const FwdParams& p, const unsigned ch
     const double2 rxa = *reinterpret_cast<const double2*>(rxc + col);
     const double2 rxb = *reinterpret_cast<const double2*>(rxc + col + 2);
     const double rx[4] = {rxa.x, rxa.y, rxb.x, rxb.y};
+    const float4 cw4 = *reinterpret_cast<const float4*>(cwf + col);   // 1 + rx^2 per column, ry^2 per row
+    const float cw[4] = {cw4.x, cw4.y, cw4.z, cw4.w};
+    const float rwv = rwf[row];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const uint32_t okm = ok[j] ? 0xffffffffu : 0u;
@@ -114,12 +124,11 @@ __device__ __forceinline__ void crop_pass1(const FwdParams& p, const unsigned ch
       saa = fma(a0, a0, fma(a1, a1, fma(a2, a2, saa)));
       const double yy = fma(y0, y0, fma(y1, y1, zd * zd));
       syy += yy;
-      // mean norms for PassT (pose_utils.py:91-92): IEEE-accurate sqrtf per point, zero for invalid pixels
+      // mean norms for PassT (pose_utils.py:91-92), float: |y| = z sqrt(1 + rx^2 + ry^2) from the float ray tables,
+      // |x| from the float NOC; one MUFU.SQRT each (1 ulp; the two means enter PassT as a ratio)
       const float x0f = f0 - 0.5f, x1f = f1 - 0.5f, x2f = f2 - 0.5f;
-      const float sy_ = sqrt_normal(ok[j] ? (float)yy : 1.0f);
-      const float sx_ = sqrt_normal(ok[j] ? fmaf(x0f, x0f, fmaf(x1f, x1f, x2f * x2f)) : 1.0f);
-      sum_ny += ok[j] ? sy_ : 0.0f;
-      sum_nx += ok[j] ? sx_ : 0.0f;
+      sum_ny = fmaf(zf, sqrt_approx(cw[j] + rwv), sum_ny);          // invalid pixels: zf == 0
+      sum_nx += and_bits(sqrt_approx(fmaf(x0f, x0f, fmaf(x1f, x1f, x2f * x2f))), okm);
     }
   }
   raw[0] = (double)cnt;
@@ -365,6 +374,8 @@ __global__ void __launch_bounds__(NT, 3) fit_ransac_crop_kernel(const FwdParams 
   double* ryr = rxc + p.W;
   float* rxf = reinterpret_cast<float*>(smem + p.off_ftab);
   float* ryf = rxf + p.W;
+  float* cwf = ryf + ((p.H + 3) & ~3);                                 // 1 + rx^2 per column (16-byte aligned), ry^2 per row
+  float* rwf = cwf + p.W;
   double* red = reinterpret_cast<double*>(smem + p.off_red);           // [NT/32][24] | mom[24] | tot[24] | cur | kept
   double* mom = red + (NT / 32) * 24;
   double* tot = mom + 24;                                              // raw totals of pass 1, kept for the record
@@ -373,7 +384,9 @@ __global__ void __launch_bounds__(NT, 3) fit_ransac_crop_kernel(const FwdParams 
   uint32_t* bits = reinterpret_cast<uint32_t*>(smem + p.off_bits);
   uint32_t* prefix = reinterpret_cast<uint32_t*>(smem + p.off_prefix);
   CropShared* sh = reinterpret_cast<CropShared*>(smem + p.off_stats);
-  double* slo = reinterpret_cast<double*>(smem + p.off_res);           // [n_hyp] lower ends of the residual intervals
+  // [n_hyp] lower ends of the residual intervals, rounded DOWN to float; they take the bitmap prefix's place (dead once
+  // the select list is built): with them, three CTAs of up to 192 threads still fit the SM's shared memory
+  float* slo = reinterpret_cast<float*>(smem + p.off_prefix);
   unsigned char* stage = smem + p.off_stages;
   uint16_t* klist = reinterpret_cast<uint16_t*>(stage + p.st_mask);    // select list, later the outlier queues
   uint16_t* band_q = klist + (p.P / 2 - kBandCap);                     // last kBandCap entries of the mask plane
@@ -425,11 +438,13 @@ __global__ void __launch_bounds__(NT, 3) fit_ransac_crop_kernel(const FwdParams 
       const double r = g.k0 * (double)(g.x0 + i) + g.k2;
       rxc[i] = r;
       rxf[i] = (float)r;
+      cwf[i] = (float)fma(r, r, 1.0);
     }
     for (int i = tid; i < p.H; i += NT) {
       const double r = g.k4 * (double)(g.y0 + i) + g.k5;
       ryr[i] = r;
       ryf[i] = (float)r;
+      rwf[i] = (float)(r * r);
     }
     __syncthreads();
     mbar_wait(&full[0], (uint32_t)(it & 1));
@@ -439,7 +454,7 @@ __global__ void __launch_bounds__(NT, 3) fit_ransac_crop_kernel(const FwdParams 
     // ---- pass 1 ----------------------------------------------------------------------------------------------------
     {
       double acc[kCropAcc];
-      crop_pass1<NT>(p, stage, rxc, ryr, bits, tid, acc);
+      crop_pass1<NT>(p, stage, rxc, ryr, cwf, rwf, bits, tid, acc);
       PF_PHASE(1);
       block_reduce<kCropAcc, NT>(acc, red, mom, tid);
     }
@@ -588,7 +603,7 @@ __global__ void __launch_bounds__(NT, 3) fit_ransac_crop_kernel(const FwdParams 
         for (int i = 0; i < 3; ++i) t[i] = (double)sf.t[i];
         const double r2 = residual_sq_iso(n_all, sh->mux, sh->muy, sh->Syy, sh->Syx, tr_sxx, A, t, (double)sf.s);
         const double e = screen_interval(sf, r2, n_all, x_rms, tr_sxx);
-        slo[h] = r2 - e;                                          // -inf: the float fit is not usable
+        slo[h] = __double2float_rd(r2 - e);                       // -inf: the float fit is not usable
         const double hi = r2 + e;
         if (hi < hi_min) hi_min = hi;
         if (p.n_hyp <= NT) {
@@ -614,7 +629,7 @@ __global__ void __launch_bounds__(NT, 3) fit_ransac_crop_kernel(const FwdParams 
     int my_cands = 0;
     if (N > 0) {
       for (int h = tid; h < p.n_hyp; h += NT) {
-        const double lo = slo[h];
+        const double lo = (double)slo[h];
         if (!(lo > U && lo >= stop2)) ++my_cands;
       }
     }
@@ -662,7 +677,7 @@ __global__ void __launch_bounds__(NT, 3) fit_ransac_crop_kernel(const FwdParams 
         const int h = base + tid;
         bool cand = false;
         if (h < p.n_hyp) {
-          const double lo = slo[h];
+          const double lo = (double)slo[h];
           cand = !(lo > U && lo >= stop2) || p.no_screen;
         }
         uint32_t cm = __ballot_sync(0xffffffffu, cand);

@@ -72,6 +72,10 @@ struct FwdParams {
   int32_t* n_valid;
   uint8_t* inlier_mask;
   int32_t* winner;
+  float* out_scale;             // optional float32 copies of the pose, written by the solve kernels
+  float* out_rot;
+  float* out_trans;
+  uint8_t* valid_mask;          // optional (plain fit): 1 where the pixel took part in the fit
   int32_t* redo_flag;           // RANSAC: set by fit_ransac_crop_kernel when fit_ransac_kernel has to do the batch (skewed K)
   double ratio_adapt;
   double pass_override, stop_override;   // > 0: use instead of the data-derived PassT / StopT (getRANSACInliers' arguments)
@@ -355,6 +359,15 @@ __device__ __forceinline__ void write_pose(const FwdParams& p, int obj, const Fi
   cx[31] = 0.0;
   p.status[obj] = status;
   p.n_valid[obj] = (int)n_valid;
+  if (p.out_scale != nullptr) p.out_scale[obj] = (float)f.s;
+  if (p.out_rot != nullptr) {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) p.out_rot[(size_t)obj * 9 + i] = (float)f.R[i];
+  }
+  if (p.out_trans != nullptr) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) p.out_trans[(size_t)obj * 3 + i] = (float)f.t[i];
+  }
 }
 
 }  // namespace posefit

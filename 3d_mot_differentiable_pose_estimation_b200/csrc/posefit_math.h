@@ -520,11 +520,12 @@ PF_HD void screen_fit32(int n, const float* sx, const float* sy, const float* sy
   for (int i = 0; i < 9; ++i) c4 = fmaf(cof[i], cof[i], c4);
   c4 *= 4.0f;
   const float b8 = 8.0f * det;
-  float lam = 1.7320508f, step = 1.0f;
+  float lam = 1.7320508f, step = 1.0f, prev = 2.0f;
 #pragma unroll 1
-  for (int it = 0; it < 24 && step > 2e-7f * lam; ++it) {   // Newton on the quartic, from above (5-6 steps; a near-double
-    const float t = fmaf(lam, lam, -1.0f);                   //  root -- s2 + s3 small -- converges linearly and takes more)
-    const float psi = fmaf(t, t, -fmaf(b8, lam, c4));
+  for (int it = 0; it < 24 && step > 1e-6f * lam && step < prev; ++it) {   // Newton on the quartic, from above: the steps
+    prev = step;                                             //  shrink monotonically until rounding takes over (5-6 steps;
+    const float t = fmaf(lam, lam, -1.0f);                   //  a near-double root -- s2 + s3 small -- converges linearly
+    const float psi = fmaf(t, t, -fmaf(b8, lam, c4));        //  and takes more)
     const float dpsi = fmaf(4.0f * lam, t, -b8);
     step = pf_div(psi, dpsi);
     lam -= step;

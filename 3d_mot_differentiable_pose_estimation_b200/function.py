@@ -49,18 +49,32 @@ def _workspace(lib, dev, b: int, h: int, w: int, n_hyp: int = 0, n_samp: int = 0
     return torch.empty(max(nbytes, 8), dtype=torch.uint8, device=dev)
 
 
+_KINV_CACHE = {}
+
+
 def default_kinv(device=None, height: int = 240, width: int = 320) -> torch.Tensor:
-    """K^-1 of the fixed MOTFront camera run_pose builds (pose_estimation.py:269-288), float64."""
-    from .synth import motfront_intrinsics
-    k = torch.linalg.inv(motfront_intrinsics(height, width)).contiguous()   # inv may return column-major strides
-    return k.to(device) if device is not None else k
+    """K^-1 of the fixed MOTFront camera run_pose builds (pose_estimation.py:269-288), float64.
+    Cached per (device, height, width): after the first call there is no host work and no host-to-device copy,
+    so `kinv=None` (the documented default of every entry here) is asynchronous and CUDA-graph capturable."""
+    dev = torch.device(device) if device is not None else torch.device('cpu')
+    if dev.type == 'cuda' and dev.index is None:
+        dev = torch.device('cuda', torch.cuda.current_device())
+    key = (dev.type, dev.index, int(height), int(width))
+    k = _KINV_CACHE.get(key)
+    if k is None:
+        from .synth import motfront_intrinsics
+        k = torch.linalg.inv(motfront_intrinsics(height, width)).contiguous()   # inv may return column-major strides
+        k = k.to(dev)
+        _KINV_CACHE[key] = k
+    return k
 
 
 def _prep_kinv(kinv, device, n_objects: int):
     if kinv is None:
-        kinv = default_kinv()
-    kinv = torch.as_tensor(kinv)
-    kinv = kinv.to(device=device, dtype=torch.float64).contiguous()
+        return default_kinv(device), 0
+    if not (isinstance(kinv, torch.Tensor) and kinv.device == device and kinv.dtype == torch.float64
+            and kinv.is_contiguous()):
+        kinv = torch.as_tensor(kinv).to(device=device, dtype=torch.float64).contiguous()
     if kinv.shape == (3, 3):
         return kinv, 0
     if kinv.shape == (n_objects, 3, 3):
@@ -86,10 +100,12 @@ def _check_crops(noc, depth, mask, bbox_xy0):
 
 
 def pose_fit_raw(noc, depth, mask, bbox_xy0, kinv=None, sample_idx=None, ratio_adapt: float = 1.0,
-                 ref_compat: bool = True) -> PoseFitRaw:
+                 ref_compat: bool = True, _f32=None, _valid_mask=None) -> PoseFitRaw:
     """Forward only, float64 records, no autograd.  Inputs: noc [B,3,H,W] f32 in [0,1],
     depth [B,H,W] f32, mask [B,H,W] u8/bool, bbox_xy0 [B,2] i32 (x0, y0 of each crop in the frame),
-    kinv [3,3] or [B,3,3] f64 (None = MOTFront camera), sample_idx [B,n_hyp,n_samp] i32 or None."""
+    kinv [3,3] or [B,3,3] f64 (None = MOTFront camera), sample_idx [B,n_hyp,n_samp] i32 or None.
+    `_f32` = (scale[B], rot[B,9], trans[B,3]) float32 tensors and `_valid_mask` [B,H,W] u8 are filled by the kernels
+    when given (the autograd operator's outputs; posefit_forward_ex / posefit_forward_ransac_ex)."""
     lib = _lib.lib()
     noc, depth, mask, bbox_xy0, b, h, w = _check_crops(noc, depth, mask, bbox_xy0)
     dev = noc.device
@@ -98,25 +114,28 @@ def pose_fit_raw(noc, depth, mask, bbox_xy0, kinv=None, sample_idx=None, ratio_a
     ctx = torch.empty(b, _lib.CTX_DOUBLES, dtype=torch.float64, device=dev)
     status = torch.empty(b, dtype=torch.int32, device=dev)
     n_valid = torch.empty(b, dtype=torch.int32, device=dev)
+    fs, fr, ft = _f32 if _f32 is not None else (None, None, None)
     with torch.cuda.device(dev):
         if sample_idx is None:
             ws = _workspace(lib, dev, b, h, w)
-            code = lib.posefit_forward(_ptr(noc), _ptr(depth), _ptr(mask), _ptr(bbox_xy0), _ptr(kinv), per_obj,
-                                       b, h, w, _ptr(pose), _ptr(ctx), _ptr(status), _ptr(n_valid), _ptr(ws),
-                                       ws.numel(), _stream(dev))
+            code = lib.posefit_forward_ex(_ptr(noc), _ptr(depth), _ptr(mask), _ptr(bbox_xy0), _ptr(kinv), per_obj,
+                                          b, h, w, _ptr(pose), _ptr(ctx), _ptr(status), _ptr(n_valid), _ptr(fs),
+                                          _ptr(fr), _ptr(ft), _ptr(_valid_mask), _ptr(ws), ws.numel(), _stream(dev))
             _lib.check(code, 'posefit_forward')
             return PoseFitRaw(pose, ctx, status, n_valid, None, None)
-        sample_idx = sample_idx.to(device=dev, dtype=torch.int32).contiguous()
+        if not (sample_idx.device == dev and sample_idx.dtype == torch.int32 and sample_idx.is_contiguous()):
+            sample_idx = sample_idx.to(device=dev, dtype=torch.int32).contiguous()
         if sample_idx.dim() != 3 or sample_idx.shape[0] != b:
             raise ValueError('sample_idx must be [B,n_hyp,n_samp]')
         n_hyp, n_samp = int(sample_idx.shape[1]), int(sample_idx.shape[2])
         inl = torch.empty(b, h, w, dtype=torch.uint8, device=dev)
         winner = torch.empty(b, dtype=torch.int32, device=dev)
         ws = _workspace(lib, dev, b, h, w, max(n_hyp, 1), n_samp)
-        code = lib.posefit_forward_ransac(_ptr(noc), _ptr(depth), _ptr(mask), _ptr(bbox_xy0), _ptr(kinv), per_obj,
-                                          _ptr(sample_idx), b, h, w, n_hyp, n_samp, float(ratio_adapt),
-                                          int(bool(ref_compat)), _ptr(pose), _ptr(ctx), _ptr(status), _ptr(n_valid),
-                                          _ptr(inl), _ptr(winner), _ptr(ws), ws.numel(), _stream(dev))
+        code = lib.posefit_forward_ransac_ex(_ptr(noc), _ptr(depth), _ptr(mask), _ptr(bbox_xy0), _ptr(kinv), per_obj,
+                                             _ptr(sample_idx), b, h, w, n_hyp, n_samp, float(ratio_adapt),
+                                             int(bool(ref_compat)), _ptr(pose), _ptr(ctx), _ptr(status),
+                                             _ptr(n_valid), _ptr(inl), _ptr(winner), _ptr(fs), _ptr(fr), _ptr(ft),
+                                             _ptr(ws), ws.numel(), _stream(dev))
         _lib.check(code, 'posefit_forward_ransac')
     return PoseFitRaw(pose, ctx, status, n_valid, inl, winner)
 
@@ -283,6 +302,32 @@ def statistical_outlier_mask(noc, depth, mask, bbox_xy0, kinv=None, source: str 
     return out
 
 
+def _forward_outputs(ctx, noc, depth, mask, bbox_xy0, kinv, sample_idx, ratio_adapt, ref_compat):
+    """Shared forward of PoseFit / PoseFitFull.  Everything the operator returns is written by the library's kernels:
+    scale / R / t as float32 by the solve kernel, the plain fit's "inlier" mask (every valid correspondence,
+    pose_estimation.py:23-25) by the moments kernel -- no eager torch arithmetic on the batch."""
+    b, _, h, w = noc.shape
+    dev = noc.device
+    if not noc.is_cuda:
+        raise _lib.PoseFitError('pose_fit needs CUDA tensors: the solver has no CPU path')
+    scale = torch.empty(b, dtype=torch.float32, device=dev)
+    rot = torch.empty(b, 3, 3, dtype=torch.float32, device=dev)
+    trans = torch.empty(b, 3, dtype=torch.float32, device=dev)
+    valid = torch.empty(b, h, w, dtype=torch.uint8, device=dev) if sample_idx is None else None
+    raw = pose_fit_raw(noc, depth, mask, bbox_xy0, kinv, sample_idx, ratio_adapt, ref_compat, _f32=(scale, rot, trans),
+                       _valid_mask=valid)
+    inl = raw.inlier_mask if raw.inlier_mask is not None else valid
+    ctx.has_inliers = raw.inlier_mask is not None
+    ctx.kinv = kinv
+    ctx.depth_grad = bool(depth.requires_grad)
+    ctx.in_dtypes = (noc.dtype, depth.dtype)
+    ctx.save_for_backward(noc, depth, mask, bbox_xy0, raw.ctx, raw.status, inl)
+    out_dtype = noc.dtype if noc.dtype.is_floating_point else torch.float32
+    if out_dtype != torch.float32:
+        scale, rot, trans = scale.to(out_dtype), rot.to(out_dtype), trans.to(out_dtype)
+    return scale, rot, trans, inl, raw
+
+
 class PoseFit(torch.autograd.Function):
     """(scale[B], R[B,3,3], t[B,3], inlier_mask[B,H,W] u8, status[B] i32, n_valid[B] i32) =
     PoseFit.apply(noc, depth, mask, bbox_xy0, kinv, sample_idx, ratio_adapt, ref_compat).
@@ -294,22 +339,8 @@ class PoseFit(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, noc, depth, mask, bbox_xy0, kinv=None, sample_idx=None, ratio_adapt=1.0, ref_compat=True):
-        raw = pose_fit_raw(noc, depth, mask, bbox_xy0, kinv, sample_idx, ratio_adapt, ref_compat)
-        b, _, h, w = noc.shape
-        inl = raw.inlier_mask
-        ctx.has_inliers = inl is not None
-        ctx.kinv = kinv
-        ctx.depth_grad = bool(depth.requires_grad)
-        ctx.in_dtypes = (noc.dtype, depth.dtype)
-        ctx.save_for_backward(noc, depth, mask, bbox_xy0, raw.ctx, raw.status,
-                              inl if inl is not None else torch.empty(0, device=noc.device))
-        out_dtype = noc.dtype if noc.dtype.is_floating_point else torch.float32
-        scale = raw.pose[:, 0].to(out_dtype)
-        rot = raw.pose[:, 1:10].reshape(b, 3, 3).to(out_dtype)
-        trans = raw.pose[:, 10:13].to(out_dtype)
-        if inl is None:
-            # plain fit: every valid correspondence takes part (mask & depth > 0, pose_estimation.py:23-25)
-            inl = ((mask != 0) & (depth > 0)).to(torch.uint8)
+        scale, rot, trans, inl, raw = _forward_outputs(ctx, noc, depth, mask, bbox_xy0, kinv, sample_idx, ratio_adapt,
+                                                       ref_compat)
         ctx.mark_non_differentiable(inl, raw.status, raw.n_valid)
         return scale, rot, trans, inl, raw.status, raw.n_valid
 
@@ -337,21 +368,8 @@ class PoseFitFull(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, noc, depth, mask, bbox_xy0, kinv=None, sample_idx=None, ratio_adapt=1.0, ref_compat=True):
-        raw = pose_fit_raw(noc, depth, mask, bbox_xy0, kinv, sample_idx, ratio_adapt, ref_compat)
-        b = noc.shape[0]
-        inl = raw.inlier_mask
-        ctx.has_inliers = inl is not None
-        ctx.kinv = kinv
-        ctx.depth_grad = bool(depth.requires_grad)
-        ctx.in_dtypes = (noc.dtype, depth.dtype)
-        ctx.save_for_backward(noc, depth, mask, bbox_xy0, raw.ctx, raw.status,
-                              inl if inl is not None else torch.empty(0, device=noc.device))
-        out_dtype = noc.dtype if noc.dtype.is_floating_point else torch.float32
-        scale = raw.pose[:, 0].to(out_dtype)
-        rot = raw.pose[:, 1:10].reshape(b, 3, 3).to(out_dtype)
-        trans = raw.pose[:, 10:13].to(out_dtype)
-        if inl is None:
-            inl = ((mask != 0) & (depth > 0)).to(torch.uint8)
+        scale, rot, trans, inl, raw = _forward_outputs(ctx, noc, depth, mask, bbox_xy0, kinv, sample_idx, ratio_adapt,
+                                                       ref_compat)
         winner = raw.winner if raw.winner is not None else torch.empty(0, dtype=torch.int32, device=noc.device)
         ctx.mark_non_differentiable(inl, raw.status, raw.n_valid, raw.pose, winner)
         return scale, rot, trans, inl, raw.status, raw.n_valid, raw.pose, winner

@@ -94,6 +94,26 @@ int posefit_forward_ransac(const float* noc, const float* depth, const uint8_t* 
                            uint8_t* inlier_mask, int32_t* winner,
                            void* workspace, size_t workspace_bytes, void* stream);
 
+/* The same two fits with the extra outputs the autograd operator wants written by the kernels themselves (no
+ * separate conversion / masking passes over the batch):  scale_f32 [B], rot_f32 [B][9], trans_f32 [B][3] -- the
+ * pose rounded to float32 by the solve kernel -- and, for the plain fit, valid_mask [B][H][W] (uint8): 1 where the
+ * pixel took part in the fit (mask != 0 and depth > 0, PoseEst/pose_estimation.py:23-25), i.e. what inlier_mask is for
+ * the RANSAC entry.  Each of them may be NULL. */
+int posefit_forward_ex(const float* noc, const float* depth, const uint8_t* mask, const int32_t* bbox_xy0,
+                       const double* kinv, int kinv_per_object, int n_objects, int height, int width,
+                       double* pose, double* ctx, int32_t* status, int32_t* n_valid,
+                       float* scale_f32, float* rot_f32, float* trans_f32, uint8_t* valid_mask,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+int posefit_forward_ransac_ex(const float* noc, const float* depth, const uint8_t* mask, const int32_t* bbox_xy0,
+                              const double* kinv, int kinv_per_object, const int32_t* sample_idx,
+                              int n_objects, int height, int width, int n_hyp, int n_samp,
+                              double ratio_adapt, int ref_compat,
+                              double* pose, double* ctx, int32_t* status, int32_t* n_valid,
+                              uint8_t* inlier_mask, int32_t* winner,
+                              float* scale_f32, float* rot_f32, float* trans_f32,
+                              void* workspace, size_t workspace_bytes, void* stream);
+
 /* Points mode: the same two fits on explicit correspondences, for callers that hold point sets
  * rather than crops -- the argument form of estimateSimilarityUmeyama / estimateSimilarityTransform
  * themselves (PoseEst/pose_utils.py:16, :86; run_pose calls them on filtered clouds,

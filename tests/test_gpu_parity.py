@@ -687,6 +687,50 @@ def test_cuda_graph_capture_and_streams(pf):
         assert torch.equal(o1, ref1) and torch.equal(o2, ref2)
 
 
+def test_public_operator_capturable_with_default_intrinsics(pf):
+    """The public autograd operator with the documented default kinv=None: after the first call there is no host work
+    (K^-1 is cached on the device), so forward + backward capture into one CUDA graph; its outputs -- float32 pose and
+    the plain fit's validity mask -- are written by the library's kernels and equal the float64 records rounded."""
+    d = pf.synth.make_objects(64, 64, 64, seed=91, device='cuda', n_hyp=32)
+    g = (torch.randn(64, device='cuda'), torch.randn(64, 3, 3, device='cuda'), torch.randn(64, 3, device='cuda'))
+    pf.pose_fit(d['noc'], d['depth'], d['mask'], d['bbox_xy0'])                 # first call builds the cache
+
+    def work(idx):
+        noc = d['noc'].detach().clone().requires_grad_(True)
+        scale, rot, trans, inl, status, n_valid = pf.pose_fit(noc, d['depth'], d['mask'], d['bbox_xy0'], sample_idx=idx)
+        ((scale * g[0]).sum() + (rot * g[1]).sum() + (trans * g[2]).sum()).backward()
+        return scale, rot, trans, inl, noc.grad
+
+    for idx in (None, d['sample_idx']):
+        eager = [t.detach().clone() for t in work(idx)]
+        torch.cuda.synchronize()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(side):
+            work(idx)
+            side.synchronize()
+            with torch.cuda.graph(graph, stream=side):
+                captured = work(idx)
+        torch.cuda.current_stream().wait_stream(side)
+        for t in captured:
+            t.detach().zero_()
+        graph.replay()
+        torch.cuda.synchronize()
+        for a, b in zip(eager, captured):
+            assert torch.equal(a, b.detach())
+        raw = pf.pose_fit_raw(d['noc'], d['depth'], d['mask'], d['bbox_xy0'], sample_idx=idx)
+        assert torch.equal(eager[0], raw.pose[:, 0].float())
+        assert torch.equal(eager[1].reshape(64, 9), raw.pose[:, 1:10].float())
+        assert torch.equal(eager[2], raw.pose[:, 10:13].float())
+        want = raw.inlier_mask if idx is not None else ((d['mask'] != 0) & (d['depth'] > 0)).to(torch.uint8)
+        assert torch.equal(eager[3], want)
+    # ragged shape / unaligned views take the generic loaders: the validity mask is still the kernel's
+    d3 = pf.synth.make_objects(5, 19, 27, seed=92, device='cuda', align_x0=1)
+    out = pf.pose_fit(d3['noc'], d3['depth'], d3['mask'], d3['bbox_xy0'])
+    assert torch.equal(out[3], ((d3['mask'] != 0) & (d3['depth'] > 0)).to(torch.uint8))
+
+
 def test_full_size_ransac_properties(pf):
     """BASELINE config 3 size (4096 x 64x64, 128 hypotheses): oracle on a 48-object sample, and
     size-independent properties on everything: inliers are a subset of the valid pixels, the
