@@ -136,103 +136,128 @@ struct BwdLoad {
   uchar4 mm, im;
 };
 
-// Streaming pass: (object, chunk) units; the 144-byte coefficient record of the NEXT unit is
-// fetched with cp.async while the current one streams, so no fp64 and no global-load latency sit
-// between units.  Two iterations of loads are issued before the first is consumed.
-template <int NT>
-__global__ void __launch_bounds__(NT, 4) fit_backward_kernel(const BwdParams p) {
+// Streaming pass: (object, chunk) units; two iterations of loads are in flight before the first is consumed.
+// Where the per-object coefficient record comes from:
+//   FUSED = false (large batches): fit_backward_coef_kernel wrote one 144-byte record per object; the record of the NEXT
+//     unit is fetched with cp.async while the current one streams;
+//   FUSED = true (small batches, where a separate 1-thread-per-object kernel is pure latency: 7 us of BASELINE config 4):
+//     one thread of the CTA computes the NEXT unit's record from the saved context (bwd_coefficients, ~300 dependent
+//     double instructions) while the other warps stream the current unit; the first unit's record is computed while
+//     L2 prefetches of the CTA's first pixels are in flight.  Units of one object recompute the same record (2-7
+//     times): nothing next to the streaming.
+template <int NT, bool FUSED, int MINB>
+__global__ void __launch_bounds__(NT, MINB) fit_backward_kernel(const BwdParams p) {
   __shared__ __align__(16) BwdCoef coefs[2];
   static_assert(sizeof(BwdCoef) == 144, "coefficient record is 9 x 16 bytes");
 #if __CUDA_ARCH__ >= 900
   if (p.early_dep & 8) asm volatile("griddepcontrol.launch_dependents;");   // the next call's first kernel may queue up
-  asm volatile("griddepcontrol.wait;" ::: "memory");            // coefficients written by fit_backward_coef_kernel
+  asm volatile("griddepcontrol.wait;" ::: "memory");            // ctx / coefficients written by the kernels before
   if (!(p.early_dep & 8)) asm volatile("griddepcontrol.launch_dependents;");
 #endif
   const int tid = threadIdx.x;
   const int n_units = p.B * p.chunks_per_obj;
-  auto fetch = [&](int unit, int buf) {
-    if (tid < 9 && unit < n_units)
-      cp_async_16(reinterpret_cast<unsigned char*>(&coefs[buf]) + 16 * tid,
-                  reinterpret_cast<const unsigned char*>(p.coef + unit / p.chunks_per_obj) + 16 * tid);
-    cp_async_commit();
+  auto provide = [&](int unit, int buf, bool me) {
+    if (FUSED) {
+      if (me && unit < n_units) {
+        BwdCoef c;
+        bwd_coefficients(p, unit / p.chunks_per_obj, c);
+        coefs[buf] = c;
+      }
+    } else {
+      if (tid < 9 && unit < n_units)
+        cp_async_16(reinterpret_cast<unsigned char*>(&coefs[buf]) + 16 * tid,
+                    reinterpret_cast<const unsigned char*>(p.coef + unit / p.chunks_per_obj) + 16 * tid);
+      cp_async_commit();
+    }
   };
-  fetch((int)blockIdx.x, 0);
+  auto load = [&](size_t ob, const float* n0p, int i, BwdLoad& d) {
+    d.a0 = __ldcs(reinterpret_cast<const float4*>(n0p + i));
+    d.a1 = __ldcs(reinterpret_cast<const float4*>(n0p + p.P + i));
+    d.a2 = __ldcs(reinterpret_cast<const float4*>(n0p + 2 * (size_t)p.P + i));
+    d.zz = __ldcs(reinterpret_cast<const float4*>(p.depth + ob + i));
+    d.mm = __ldcs(reinterpret_cast<const uchar4*>(p.mask + ob + i));
+    d.im = make_uchar4(1, 1, 1, 1);
+    if (p.inlier_mask) d.im = __ldcs(reinterpret_cast<const uchar4*>(p.inlier_mask + ob + i));
+  };
+  if (!FUSED) provide((int)blockIdx.x, 0, false);
   int k = 0;
   for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++k) {
     const int obj = unit / p.chunks_per_obj;
     const int ch = unit - obj * p.chunks_per_obj;
-    cp_async_wait_all();
-    __syncthreads();                                   // this unit's record is visible; the other buffer is free
-    fetch(unit + (int)gridDim.x, (k + 1) & 1);
-    const BwdCoef c = coefs[k & 1];
     const int px0 = ch * p.chunk_px;
     const int px1 = min(px0 + p.chunk_px, p.P);
     const size_t ob = (size_t)obj * p.P;
     const float* n0p = p.noc + ob * 3;
-    const float* n1p = n0p + p.P;
-    const float* n2p = n1p + p.P;
     float* g0p = p.grad_noc + ob * 3;
     float* g1p = g0p + p.P;
     float* g2p = g1p + p.P;
+    if (FUSED && k == 0) {
+      // a CTA's first unit: its pixels are pulled into L2 (no registers held) while thread 0 computes the record
+      if (p.vec_ok) {
+        for (int ii = px0 + 4 * tid; ii < px1; ii += 4 * NT) {
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(n0p + ii));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(n0p + p.P + ii));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(n0p + 2 * (size_t)p.P + ii));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(p.depth + ob + ii));
+        }
+      }
+      provide(unit, 0, tid == 0);
+    }
+    if (!FUSED) cp_async_wait_all();
+    __syncthreads();                                   // this unit's record is visible; the other buffer is free
+    provide(unit + (int)gridDim.x, (k + 1) & 1, tid == 32 * ((k + 1) & (NT / 32 - 1)));
+    const BwdCoef c = coefs[k & 1];
     if (p.vec_ok) {
-      auto load = [&](int i, BwdLoad& d) {
-        d.a0 = __ldcs(reinterpret_cast<const float4*>(n0p + i));
-        d.a1 = __ldcs(reinterpret_cast<const float4*>(n1p + i));
-        d.a2 = __ldcs(reinterpret_cast<const float4*>(n2p + i));
-        d.zz = __ldcs(reinterpret_cast<const float4*>(p.depth + ob + i));
-        d.mm = __ldcs(reinterpret_cast<const uchar4*>(p.mask + ob + i));
-        d.im = make_uchar4(1, 1, 1, 1);
-        if (p.inlier_mask) d.im = __ldcs(reinterpret_cast<const uchar4*>(p.inlier_mask + ob + i));
-      };
-      auto emit = [&](int i, const BwdLoad& d) {
+      auto emit = [&](int ii, const BwdLoad& d) {
         float4 go0, go1, go2, gz;
-        const int row = i / p.W, col = i - row * p.W;
+        const int row = ii / p.W, col = ii - row * p.W;
         bwd_point(c, d.a0.x, d.a1.x, d.a2.x, d.zz.x, d.mm.x && d.im.x && d.zz.x > 0.0f, row, col + 0, go0.x, go1.x, go2.x, gz.x);
         bwd_point(c, d.a0.y, d.a1.y, d.a2.y, d.zz.y, d.mm.y && d.im.y && d.zz.y > 0.0f, row, col + 1, go0.y, go1.y, go2.y, gz.y);
         bwd_point(c, d.a0.z, d.a1.z, d.a2.z, d.zz.z, d.mm.z && d.im.z && d.zz.z > 0.0f, row, col + 2, go0.z, go1.z, go2.z, gz.z);
         bwd_point(c, d.a0.w, d.a1.w, d.a2.w, d.zz.w, d.mm.w && d.im.w && d.zz.w > 0.0f, row, col + 3, go0.w, go1.w, go2.w, gz.w);
-        __stcs(reinterpret_cast<float4*>(g0p + i), go0);
-        __stcs(reinterpret_cast<float4*>(g1p + i), go1);
-        __stcs(reinterpret_cast<float4*>(g2p + i), go2);
-        if (p.grad_depth) __stcs(reinterpret_cast<float4*>(p.grad_depth + ob + i), gz);
+        __stcs(reinterpret_cast<float4*>(g0p + ii), go0);
+        __stcs(reinterpret_cast<float4*>(g1p + ii), go1);
+        __stcs(reinterpret_cast<float4*>(g2p + ii), go2);
+        if (p.grad_depth) __stcs(reinterpret_cast<float4*>(p.grad_depth + ob + ii), gz);
       };
       if (c.live) {
+        BwdLoad d0, d1;
         int i = px0 + 4 * tid;
         for (; i + 4 * NT < px1; i += 8 * NT) {          // two iterations in flight
-          BwdLoad d0, d1;
-          load(i, d0);
-          load(i + 4 * NT, d1);
+          load(ob, n0p, i, d0);
+          load(ob, n0p, i + 4 * NT, d1);
           emit(i, d0);
           emit(i + 4 * NT, d1);
         }
         if (i < px1) {
-          BwdLoad d0;
-          load(i, d0);
+          load(ob, n0p, i, d0);
           emit(i, d0);
         }
       } else {
         const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int i = px0 + 4 * tid; i < px1; i += 4 * NT) {
-          __stcs(reinterpret_cast<float4*>(g0p + i), zero);
-          __stcs(reinterpret_cast<float4*>(g1p + i), zero);
-          __stcs(reinterpret_cast<float4*>(g2p + i), zero);
-          if (p.grad_depth) __stcs(reinterpret_cast<float4*>(p.grad_depth + ob + i), zero);
+        for (int ii = px0 + 4 * tid; ii < px1; ii += 4 * NT) {
+          __stcs(reinterpret_cast<float4*>(g0p + ii), zero);
+          __stcs(reinterpret_cast<float4*>(g1p + ii), zero);
+          __stcs(reinterpret_cast<float4*>(g2p + ii), zero);
+          if (p.grad_depth) __stcs(reinterpret_cast<float4*>(p.grad_depth + ob + ii), zero);
         }
       }
     } else {
-      for (int i = px0 + tid; i < px1; i += NT) {
+      const float* n1p = n0p + p.P;
+      const float* n2p = n1p + p.P;
+      for (int ii = px0 + tid; ii < px1; ii += NT) {
         float o0 = 0, o1 = 0, o2 = 0, oz = 0;
         if (c.live) {
-          const float z = p.depth[ob + i];
-          bool w = p.mask[ob + i] != 0 && z > 0.0f;
-          if (p.inlier_mask) w = w && p.inlier_mask[ob + i] != 0;
-          const int row = i / p.W, col = i - row * p.W;
-          bwd_point(c, n0p[i], n1p[i], n2p[i], z, w, row, col, o0, o1, o2, oz);
+          const float z = p.depth[ob + ii];
+          bool w = p.mask[ob + ii] != 0 && z > 0.0f;
+          if (p.inlier_mask) w = w && p.inlier_mask[ob + ii] != 0;
+          const int row = ii / p.W, col = ii - row * p.W;
+          bwd_point(c, n0p[ii], n1p[ii], n2p[ii], z, w, row, col, o0, o1, o2, oz);
         }
-        g0p[i] = o0;
-        g1p[i] = o1;
-        g2p[i] = o2;
-        if (p.grad_depth) p.grad_depth[ob + i] = oz;
+        g0p[ii] = o0;
+        g1p[ii] = o1;
+        g2p[ii] = o2;
+        if (p.grad_depth) p.grad_depth[ob + ii] = oz;
       }
     }
   }

@@ -182,7 +182,7 @@ def points_fit_raw(src, dst, mask=None, sample_idx=None, ratio_adapt: float = 1.
 
 
 def pose_fit_backward_raw(noc, depth, mask, inlier_mask, bbox_xy0, kinv, ctx, status, grad_scale, grad_R, grad_t,
-                          want_depth_grad: bool = False):
+                          want_depth_grad: bool = False, out=None):
     """NOC (and optionally depth) gradient from the saved context.  All tensors on one CUDA device."""
     lib = _lib.lib()
     noc, depth, mask, bbox_xy0, b, h, w = _check_crops(noc, depth, mask, bbox_xy0)
@@ -195,7 +195,7 @@ def pose_fit_backward_raw(noc, depth, mask, inlier_mask, bbox_xy0, kinv, ctx, st
         return t.detach().to(device=dev, dtype=torch.float32).reshape(shape).contiguous()
 
     grad_scale, grad_R, grad_t = f32(grad_scale, (b,)), f32(grad_R, (b, 9)), f32(grad_t, (b, 3))
-    g_noc = torch.empty_like(noc)
+    g_noc = out if out is not None else torch.empty_like(noc)      # (out: a caller-owned [B,3,H,W] f32 buffer)
     g_depth = torch.empty_like(depth) if want_depth_grad else None
     if inlier_mask is not None:
         inlier_mask = inlier_mask.to(torch.uint8).contiguous()

@@ -40,12 +40,17 @@ def parse():
     ap.add_argument('--steps', type=int, default=100)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--objects', type=int, default=SEQ_PER_GPU * FRAMES_PER_SEQ * OBJ_PER_FRAME,
-                    help='objects per GPU per step (default: config-5 shard, 125000)')
+    ap.add_argument('--objects', type=int, default=0,
+                    help='objects per GPU per step (default: weak = the config-5 shard at 8 GPUs, 125000; strong = '
+                         '1,000,000 / N)')
+    ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
+                    help='weak: 125000 objects per GPU whatever N (default); strong: config 5 as written -- 1M objects in '
+                         'total, 1M / N per GPU')
     ap.add_argument('--size', type=int, default=64)
     ap.add_argument('--e2e-objects', type=int, default=16384)
     ap.add_argument('--cpu-sample', type=int, default=0, help='objects in the CPU baseline sample (0 = auto)')
     ap.add_argument('--no-extra', action='store_true', help='skip the config 2/3/4 side measurements')
+    ap.add_argument('--no-full', action='store_true', help='skip the 1M-object single-GPU config-5 measurement (N = 1)')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     return ap.parse_args()
 
@@ -53,19 +58,73 @@ def parse():
 # ----------------------------------------------------------------------------------------------
 # CPU legs (oracle = NumPy restatement of the reference; the reference itself is NumPy)
 # ----------------------------------------------------------------------------------------------
+def _reference_modules():
+    """(pose_utils, pose_estimation) of the UNMODIFIED reference -- /root/reference in the build container, the copy
+    oracle/Makefile staged under oracle/_ref/ on the GPU box -- or None (then the NumPy port is timed)."""
+    if os.environ.get('POSEFIT_CPU_PORT'):
+        return None
+    try:
+        from oracle import ref_import
+        if not ref_import.reference_available():
+            return None
+        return ref_import.load_reference()
+    except Exception as e:      # noqa: BLE001
+        print('bench: reference modules not importable (%r), timing the port' % (e,), file=sys.stderr)
+        return None
+
+
+def cpu_kind():
+    return 'reference' if _reference_modules() is not None else 'port'
+
+
 def _cpu_worker(job):
     os.environ.setdefault('OMP_NUM_THREADS', '1')
+    import contextlib
+    import io
     import numpy as np
     import torch
     torch.set_num_threads(1)
     from oracle import grad_oracle
     from oracle import posefit_oracle as po
-    noc, depth, mask, xy0, idx, with_bwd = job
+    noc, depth, mask, xy0, idx, with_bwd, core = job
+    if core is not None and hasattr(os, 'sched_setaffinity'):
+        try:
+            os.sched_setaffinity(0, {core})
+        except OSError:
+            pass
+    ref = _reference_modules()
+    if ref is not None:
+        from oracle import ref_import
+        pu, pe = ref
+        intr = po.motfront_intrinsics()
     t0 = time.perf_counter()
     n = noc.shape[0]
     for i in range(n):
         h, w = depth[i].shape
         x0, y0 = int(xy0[i, 0]), int(xy0[i, 1])
+        if ref is not None:
+            # the per-instance flow of run_pose (pose_estimation.py:256-290, :323, :363) on the reference's own functions
+            depth_pad = np.zeros((po.FRAME_H, po.FRAME_W))                          # :260-262 (float64 pads)
+            depth_pad[y0:y0 + h, x0:x0 + w] = depth[i]
+            mask_pad = np.zeros((po.FRAME_H, po.FRAME_W), dtype=bool)
+            mask_pad[y0:y0 + h, x0:x0 + w] = mask[i] != 0
+            noc_pad = np.zeros((po.FRAME_H, po.FRAME_W, 3))                         # :265-267
+            noc_pad[y0:y0 + h, x0:x0 + w, :] = np.transpose(noc[i], (1, 2, 0))
+            depth_pts, idxs = pe.backproject(depth_pad, intr, mask_pad)             # :290
+            noc_pts = noc_pad[idxs[0], idxs[1], :] - 0.5                            # :323
+            ok, inl = depth_pts.shape[0] > 0, None
+            if ok and idx is None:
+                src = np.transpose(np.hstack([noc_pts, np.ones([noc_pts.shape[0], 1])]))
+                dst = np.transpose(np.hstack([depth_pts, np.ones([noc_pts.shape[0], 1])]))
+                pu.estimateSimilarityUmeyama(src, dst)                              # pose_utils.py:16-61
+            elif ok:
+                with ref_import.replay_randint(idx[i], pu), contextlib.redirect_stdout(io.StringIO()):
+                    ok = pu.estimateSimilarityTransform(noc_pts, depth_pts)[0] is not None   # :86-117
+            if with_bwd and ok:
+                wts = np.ones(noc_pts.shape[0])
+                grad_oracle.fit_gradients(torch.from_numpy(noc_pts), torch.from_numpy(depth_pts), torch.from_numpy(wts),
+                                          1.0, torch.ones(3, 3, dtype=torch.float64), torch.ones(3, dtype=torch.float64))
+            continue
         fd = np.zeros((po.FRAME_H, po.FRAME_W), dtype=np.float32)
         fm = np.zeros((po.FRAME_H, po.FRAME_W), dtype=bool)
         fd[y0:y0 + h, x0:x0 + w] = depth[i]
@@ -81,8 +140,9 @@ def _cpu_worker(job):
     return n, time.perf_counter() - t0
 
 
-def cpu_objects_per_s(sample, with_bwd=True, ransac=False, procs=None):
-    """Times the oracle over `sample` objects spread over `procs` processes; returns (obj/s, procs)."""
+def cpu_objects_per_s(sample, with_bwd=True, ransac=False, procs=None, pin=False):
+    """Times the CPU path over `sample` objects spread over `procs` processes; returns (obj/s, procs).  pin: bind the
+    (single) worker to one core with sched_setaffinity."""
     import multiprocessing as mp
     import numpy as np
     procs = procs or (os.cpu_count() or 1)
@@ -92,11 +152,13 @@ def cpu_objects_per_s(sample, with_bwd=True, ransac=False, procs=None):
     n = noc.shape[0]
     procs = max(1, min(procs, n))
     cuts = np.linspace(0, n, procs + 1).astype(int)
-    jobs = [(noc[a:b], depth[a:b], mask[a:b], xy0[a:b], None if idx is None else idx[a:b], with_bwd)
+    cores = sorted(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else [0]
+    jobs = [(noc[a:b], depth[a:b], mask[a:b], xy0[a:b], None if idx is None else idx[a:b], with_bwd,
+             cores[0] if (pin and procs == 1) else None)
             for a, b in zip(cuts[:-1], cuts[1:]) if b > a]
     ctx = mp.get_context('spawn')
     with ctx.Pool(len(jobs)) as pool:
-        pool.map(_cpu_worker, [(noc[:1], depth[:1], mask[:1], xy0[:1], None if idx is None else idx[:1], with_bwd)]
+        pool.map(_cpu_worker, [(noc[:1], depth[:1], mask[:1], xy0[:1], None if idx is None else idx[:1], with_bwd, None)]
                  * len(jobs))                                     # import / warm-up
         t0 = time.perf_counter()
         pool.map(_cpu_worker, jobs)
@@ -118,23 +180,27 @@ def _subsample(sample, n):
     return {k: v[:n] for k, v in sample.items()}
 
 
-def cpu_baseline(pf, size, n_sample, kind='port'):
-    """Headline baseline: fwd+bwd on all host cores; plus one core, and the forward-only / RANSAC
+def cpu_baseline(pf, size, n_sample):
+    """Headline baseline: fwd+bwd on all host cores; plus one pinned core, and the forward-only / RANSAC
     variants of configs 2 and 3 (each a bounded sample, stated)."""
+    kind = cpu_kind()
     sample = pf.synth.make_objects(n_sample, size, size, seed=9001, n_hyp=128)
     value, cores = cpu_objects_per_s(sample, with_bwd=True)
     n1 = max(8, n_sample // max(cores, 1))
-    one, _ = cpu_objects_per_s(_subsample(sample, n1), with_bwd=True, procs=1)
+    one, _ = cpu_objects_per_s(_subsample(sample, n1), with_bwd=True, procs=1, pin=True)
     fwd, _ = cpu_objects_per_s(sample, with_bwd=False)
     n_r = max(cores, min(n_sample, 48 * cores))
     rans, _ = cpu_objects_per_s(_subsample(sample, n_r), with_bwd=False, ransac=True)
+    what = ('the UNMODIFIED reference functions (PoseEst backproject on the padded 240x320 arrays + NOC gather + '
+            'estimateSimilarityUmeyama / estimateSimilarityTransform with replayed np.random.randint)' if kind == 'reference'
+            else 'the NumPy port of the reference (oracle/posefit_oracle.py)')
     return {'value': value, 'unit': UNIT, 'cores': cores, 'kind': kind, 'cpu_model': cpu_model(),
-            'single_core_value': one,
+            'single_core_value': one, 'single_core_pinned': hasattr(os, 'sched_setaffinity'),
             'config2_fwd_plain_value': fwd, 'config3_ransac128_value': rans,
-            'sample': f'{n_sample} objects of the same {size}x{size} workload, fwd (NumPy restatement of '
-                      f'backproject+Umeyama, fp64) + bwd (fp64 torch-autograd restatement), {cores} processes x 1 '
-                      f'thread; single core on {n1} objects; config 2 (fwd only) on {n_sample}, config 3 '
-                      f'(RANSAC 128 hyp, replayed indices) on {n_r} objects'}
+            'sample': f'{n_sample} objects of the same {size}x{size} workload, fwd = {what}, fp64; bwd = fp64 torch-autograd '
+                      f'restatement (the reference has no backward); {cores} processes x 1 thread; single core '
+                      f'(sched_setaffinity) on {n1} objects; config 2 (fwd only) on {n_sample}, config 3 (RANSAC 128 hyp, '
+                      f'replayed indices) on {n_r} objects'}
 
 
 # ----------------------------------------------------------------------------------------------
@@ -229,10 +295,31 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------------------
+TOTAL_OBJECTS = 1000000                                        # config 5
+
+
+def objects_per_gpu(args, world):
+    if args.objects > 0:
+        return args.objects
+    if args.scaling == 'strong':
+        return TOTAL_OBJECTS // max(world, 1) // (FRAMES_PER_SEQ * OBJ_PER_FRAME) * (FRAMES_PER_SEQ * OBJ_PER_FRAME)
+    return SEQ_PER_GPU * FRAMES_PER_SEQ * OBJ_PER_FRAME
+
+
 def workload_name(n_obj, size):
     """config.workload, shared by both arms."""
-    return (f'config-5 shard: {n_obj} objects/GPU ({SEQ_PER_GPU} sequences x {FRAMES_PER_SEQ} frames x {OBJ_PER_FRAME} '
-            f'objects) x {size}x{size} NOC+depth+mask crops, plain Umeyama fit fwd + bwd, sharded by sequence')
+    return (f'config-5 shard: {n_obj} objects/GPU ({n_obj // (FRAMES_PER_SEQ * OBJ_PER_FRAME)} sequences x {FRAMES_PER_SEQ} '
+            f'frames x {OBJ_PER_FRAME} objects) x {size}x{size} NOC+depth+mask crops, plain Umeyama fit fwd + bwd, '
+            f'sharded by sequence')
+
+
+def config_dict(args, n_obj, size):
+    """The `config` object -- identical keys and values in both arms (our CUDA path and the CPU reference arm)."""
+    P = size * size
+    return {'workload': workload_name(n_obj, size), 'objects_per_gpu': n_obj, 'crop': [size, size],
+            'scaling': args.scaling,
+            'l2': 'inputs per step (%.1f GB) exceed the 126 MB L2; no flush needed' % (n_obj * 17 * P / 1e9),
+            'collective': 'all-gather of the 128-B pose records per step (N > 1; none at N = 1)'}
 
 
 def peaks():
@@ -277,7 +364,7 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
     hbm_peak, peak_src = peaks()
-    size, n_obj = args.size, args.objects
+    size, n_obj = args.size, objects_per_gpu(args, world)
     P = size * size
 
     def ev():
@@ -539,6 +626,72 @@ def run_ours(args):
                                             'l2': l2_note % (8, 8 * b4 / 1e6)}
         del c4s
 
+        # ---- the PUBLIC autograd operator on the headline shard: PoseFit.apply + backward (same inputs, same upstream
+        # gradients through a linear loss); everything on the device side is the library's kernels
+        g_R33 = g_R.reshape(n_obj, 3, 3)
+
+        def api_step():
+            noc = d['noc'].requires_grad_(True)
+            noc.grad = None
+            scale, rot, trans, _, _, _ = pf.pose_fit(noc, d['depth'], d['mask'], d['bbox_xy0'])
+            torch.autograd.backward((scale, rot, trans), (g_s, g_R33, g_t))
+            return noc.grad
+        for _ in range(3):
+            api_step()
+        torch.cuda.synchronize()
+        k_api = max(3, min(args.steps, 20))
+        a0, a1 = ev(), ev()
+        a0.record()
+        for _ in range(k_api):
+            api_step()
+        a1.record()
+        torch.cuda.synchronize()
+        ms_api = a0.elapsed_time(a1) / k_api
+        d['noc'].requires_grad_(False)
+        b_api = n_obj * (18 * P + 64) + bytes_bwd               # + 1 B/px: the validity mask the operator returns
+        configs['C5 shard via PoseFit.apply + backward'] = {
+            'ms': ms_api, 'objects_per_s': n_obj / ms_api * 1e3, 'gbs': b_api / ms_api / 1e6,
+            'frac': b_api / ms_api / 1e6 / hbm_peak, 'vs_raw_api': ms_api / ms,
+            'note': 'public torch.autograd.Function (pose_fit, kinv=None) + backward, eager launches; algorithmic bytes '
+                    'include the 1 B/px validity mask the operator returns'}
+
+        # ---- config 5 as written: 1,000,000 objects on ONE GPU (69.6 GB of inputs + 49 GB of NOC gradient)
+        if world == 1 and not args.no_full and n_obj < TOTAL_OBJECTS:
+            free_b, _ = torch.cuda.mem_get_info()
+            need = TOTAL_OBJECTS * (29 * P + 512)
+            if free_b > need * 1.05:
+                d.clear()
+                torch.cuda.empty_cache()
+                big = pf.synth.make_objects(TOTAL_OBJECTS, size, size, seed=5100, device=dev)
+                gb = torch.Generator(device=dev).manual_seed(78)
+                bg = (torch.randn(TOTAL_OBJECTS, device=dev, generator=gb), torch.randn(TOTAL_OBJECTS, 9, device=dev, generator=gb),
+                      torch.randn(TOTAL_OBJECTS, 3, device=dev, generator=gb))
+                g_noc = torch.empty_like(big['noc'])
+
+                def big_step():
+                    raw = pf.pose_fit_raw(big['noc'], big['depth'], big['mask'], big['bbox_xy0'], kinv)
+                    pf.pose_fit_backward_raw(big['noc'], big['depth'], big['mask'], None, big['bbox_xy0'], kinv, raw.ctx,
+                                             raw.status, *bg, out=g_noc)
+                for _ in range(2):
+                    big_step()
+                torch.cuda.synchronize()
+                k_big = 5
+                a0, a1 = ev(), ev()
+                a0.record()
+                for _ in range(k_big):
+                    big_step()
+                a1.record()
+                torch.cuda.synchronize()
+                ms_big = a0.elapsed_time(a1) / k_big
+                b_big = TOTAL_OBJECTS * (17 * P + 64 + 29 * P + 52)
+                configs['C5 1M @ N=1'] = {'ms': ms_big, 'objects_per_s': TOTAL_OBJECTS / ms_big * 1e3,
+                                          'gbs': b_big / ms_big / 1e6, 'frac': b_big / ms_big / 1e6 / hbm_peak,
+                                          'steps': k_big, 'note': 'BASELINE config 5 on one GPU: 1,000,000 objects fwd + bwd per step'}
+                del big, bg, g_noc
+                torch.cuda.empty_cache()
+            else:
+                configs['C5 1M @ N=1'] = {'skipped': 'needs %.0f GB of device memory, %.0f GB free' % (need / 1e9, free_b / 1e9)}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         n_cpu = args.cpu_sample or 256 * (os.cpu_count() or 1)
@@ -547,18 +700,16 @@ def run_ours(args):
     if rank == 0:
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
-            'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak',
+            'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': args.scaling,
             'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-            'config': {'workload': workload_name(n_obj, size),
-                       'objects_per_gpu': n_obj, 'crop': [size, size],
-                       'l2': 'inputs per step (%.1f GB) exceed the 126 MB L2; no flush needed' % (n_obj * 17 * P / 1e9),
-                       'collective': {'none': 'none',
-                                      'peer': 'all-gather of 128-B pose records per step over NVLink peer memory '
-                                              '(symmetric memory, copy engines) beside the backward pass',
-                                      'sync': 'NCCL all_gather of 128-B pose records per step, after the backward pass',
-                                      'async': 'NCCL all_gather of 128-B pose records per step, beside the backward pass'
-                                      }[gather_mode],
-                       'host_numa_node': numa_node},
+            'config': config_dict(args, n_obj, size),
+            'run': {'collective': {'none': 'none',
+                                   'peer': 'all-gather of 128-B pose records per step over NVLink peer memory '
+                                           '(symmetric memory, copy engines) beside the backward pass',
+                                   'sync': 'NCCL all_gather of 128-B pose records per step, after the backward pass',
+                                   'async': 'NCCL all_gather of 128-B pose records per step, beside the backward pass'
+                                   }[gather_mode],
+                    'host_numa_node': numa_node},
             'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': int(launches),
             'clocks': clk.summary(), 'configs': configs,
         }
@@ -569,27 +720,34 @@ def run_ours(args):
 
 
 def run_reference(args):
+    """The reference's own CPU implementation of the path on this box's host cores (all of them), on a bounded sample
+    of the same workload per step.  kind = "reference": the unmodified PoseEst functions staged under oracle/_ref (or
+    /root/reference); "port": oracle/posefit_oracle.py when they are not there."""
     rank = int(os.environ.get('RANK', 0))
     if rank != 0:
         return
+    world = int(os.environ.get('WORLD_SIZE', args.gpus or 1))
     pf_synth = importlib.import_module(f'{PKG}.synth')
     cores = os.cpu_count() or 1
     n = args.cpu_sample or 32 * cores
+    n_obj = objects_per_gpu(args, world)
+    kind = cpu_kind()
     sample = pf_synth.make_objects(n, args.size, args.size, seed=9001)
     vals = []
     for _ in range(max(1, min(args.steps, 3))):
         v, used = cpu_objects_per_s(sample, with_bwd=True)
         vals.append(v)
     value = sorted(vals)[len(vals) // 2]
-    what = (f'{n} objects per step of the same {args.size}x{args.size} workload; oracle port (NumPy restatement of '
-            f'PoseEst backproject + estimateSimilarityUmeyama, fp64) + fp64 autograd backward, {used} processes')
+    fwd = ('the unmodified PoseEst backproject + NOC gather + estimateSimilarityUmeyama (fp64)' if kind == 'reference'
+           else 'oracle port (NumPy restatement of PoseEst backproject + estimateSimilarityUmeyama, fp64)')
+    what = (f'{n} objects per step of the same {args.size}x{args.size} workload (bounded sample, same generator); fwd = {fwd}; '
+            f'bwd = fp64 torch-autograd restatement (the reference has no backward); {used} processes x 1 thread')
     line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': n / value * 1e3, 'higher_is_better': True,
-            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-            'config': {'workload': workload_name(args.objects, args.size), 'objects_per_gpu': args.objects,
-                       'crop': [args.size, args.size],
-                       'sample': f'{n} objects of that workload per step (CPU arm: bounded sample, same generator)'},
-            'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': used, 'kind': 'port', 'sample': what},
+            'scaling': args.scaling, 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': config_dict(args, n_obj, args.size),
+            'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': used, 'kind': kind, 'cpu_model': cpu_model(),
+                             'sample': what},
             'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
     print(json.dumps(line))

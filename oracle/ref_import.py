@@ -2,8 +2,8 @@
 
 TEST INFRASTRUCTURE.  `/root/reference` does not exist on the GPU box, so nothing that
 runs there may call this; it is used by `oracle/gen_golden.py` (which writes the committed
-fixtures under tests/golden/) and by the optional `tests/test_oracle_vs_reference.py`
-cross-check, which skips when the tree is absent.
+fixtures under tests/golden/); bench.py's CPU arm imports the same modules from the copy that
+`oracle/Makefile` stages under oracle/_ref/ (git-ignored; it travels to the GPU box).
 
 `PoseEst/pose_estimation.py` imports open3d / matplotlib / detectron2 / easydict at module
 scope (pose_estimation.py:5-12); none is installed here and none is touched by
@@ -19,7 +19,17 @@ import types
 
 import numpy as np
 
-REFERENCE_ROOT = os.environ.get('POSEFIT_REFERENCE_ROOT', '/root/reference')
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), '_ref')      # oracle/Makefile copies the files here
+
+
+def _default_root() -> str:
+    """/root/reference in the build container; on the GPU box (no reference tree) the copy oracle/Makefile staged."""
+    if os.path.isfile(os.path.join('/root/reference', 'PoseEst', 'pose_utils.py')):
+        return '/root/reference'
+    return _STAGED
+
+
+REFERENCE_ROOT = os.environ.get('POSEFIT_REFERENCE_ROOT') or _default_root()
 
 
 def reference_available() -> bool:
