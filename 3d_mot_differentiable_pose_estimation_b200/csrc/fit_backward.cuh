@@ -136,39 +136,29 @@ struct BwdLoad {
   uchar4 mm, im;
 };
 
-// Streaming pass: (object, chunk) units; two iterations of loads are in flight before the first is consumed.
-// Where the per-object coefficient record comes from:
-//   FUSED = false (large batches): fit_backward_coef_kernel wrote one 144-byte record per object; the record of the NEXT
-//     unit is fetched with cp.async while the current one streams;
-//   FUSED = true (small batches, where a separate 1-thread-per-object kernel is pure latency: 7 us of BASELINE config 4):
-//     one thread of the CTA computes the NEXT unit's record from the saved context (bwd_coefficients, ~300 dependent
-//     double instructions) while the other warps stream the current unit; the first unit's record is computed while
-//     L2 prefetches of the CTA's first pixels are in flight.  Units of one object recompute the same record (2-7
-//     times): nothing next to the streaming.
-template <int NT, bool FUSED, int MINB>
+// Streaming pass: (object, chunk) units; the 144-byte coefficient record of the NEXT unit is fetched with cp.async
+// while the current one streams, so no fp64 and no global-load latency sit between units.  Two iterations of loads
+// are issued before the first is consumed.  MINB = 3: 80 registers, nothing spilled, 24 warps per SM -- measured
+// 6.19 TB/s on the config-5 shard against 5.88 TB/s for MINB = 4 (64 registers, 36 bytes of spills, 32 warps).
+// (Computing the record inside this kernel instead of fit_backward_coef_kernel -- one thread per CTA, behind the
+// streaming of the previous unit -- was built and measured on BASELINE config 4: 64.7 us against 64.9 us, i.e. the
+// separate kernel already hides behind the programmatic dependent launch; not kept.)
+template <int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB) fit_backward_kernel(const BwdParams p) {
   __shared__ __align__(16) BwdCoef coefs[2];
   static_assert(sizeof(BwdCoef) == 144, "coefficient record is 9 x 16 bytes");
 #if __CUDA_ARCH__ >= 900
   if (p.early_dep & 8) asm volatile("griddepcontrol.launch_dependents;");   // the next call's first kernel may queue up
-  asm volatile("griddepcontrol.wait;" ::: "memory");            // ctx / coefficients written by the kernels before
+  asm volatile("griddepcontrol.wait;" ::: "memory");            // coefficients written by fit_backward_coef_kernel
   if (!(p.early_dep & 8)) asm volatile("griddepcontrol.launch_dependents;");
 #endif
   const int tid = threadIdx.x;
   const int n_units = p.B * p.chunks_per_obj;
-  auto provide = [&](int unit, int buf, bool me) {
-    if (FUSED) {
-      if (me && unit < n_units) {
-        BwdCoef c;
-        bwd_coefficients(p, unit / p.chunks_per_obj, c);
-        coefs[buf] = c;
-      }
-    } else {
-      if (tid < 9 && unit < n_units)
-        cp_async_16(reinterpret_cast<unsigned char*>(&coefs[buf]) + 16 * tid,
-                    reinterpret_cast<const unsigned char*>(p.coef + unit / p.chunks_per_obj) + 16 * tid);
-      cp_async_commit();
-    }
+  auto provide = [&](int unit, int buf) {
+    if (tid < 9 && unit < n_units)
+      cp_async_16(reinterpret_cast<unsigned char*>(&coefs[buf]) + 16 * tid,
+                  reinterpret_cast<const unsigned char*>(p.coef + unit / p.chunks_per_obj) + 16 * tid);
+    cp_async_commit();
   };
   auto load = [&](size_t ob, const float* n0p, int i, BwdLoad& d) {
     d.a0 = __ldcs(reinterpret_cast<const float4*>(n0p + i));
@@ -179,7 +169,7 @@ __global__ void __launch_bounds__(NT, MINB) fit_backward_kernel(const BwdParams 
     d.im = make_uchar4(1, 1, 1, 1);
     if (p.inlier_mask) d.im = __ldcs(reinterpret_cast<const uchar4*>(p.inlier_mask + ob + i));
   };
-  if (!FUSED) provide((int)blockIdx.x, 0, false);
+  provide((int)blockIdx.x, 0);
   int k = 0;
   for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++k) {
     const int obj = unit / p.chunks_per_obj;
@@ -191,21 +181,9 @@ __global__ void __launch_bounds__(NT, MINB) fit_backward_kernel(const BwdParams 
     float* g0p = p.grad_noc + ob * 3;
     float* g1p = g0p + p.P;
     float* g2p = g1p + p.P;
-    if (FUSED && k == 0) {
-      // a CTA's first unit: its pixels are pulled into L2 (no registers held) while thread 0 computes the record
-      if (p.vec_ok) {
-        for (int ii = px0 + 4 * tid; ii < px1; ii += 4 * NT) {
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(n0p + ii));
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(n0p + p.P + ii));
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(n0p + 2 * (size_t)p.P + ii));
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(p.depth + ob + ii));
-        }
-      }
-      provide(unit, 0, tid == 0);
-    }
-    if (!FUSED) cp_async_wait_all();
+    cp_async_wait_all();
     __syncthreads();                                   // this unit's record is visible; the other buffer is free
-    provide(unit + (int)gridDim.x, (k + 1) & 1, tid == 32 * ((k + 1) & (NT / 32 - 1)));
+    provide(unit + (int)gridDim.x, (k + 1) & 1);
     const BwdCoef c = coefs[k & 1];
     if (p.vec_ok) {
       auto emit = [&](int ii, const BwdLoad& d) {

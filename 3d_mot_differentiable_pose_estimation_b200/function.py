@@ -302,7 +302,7 @@ def statistical_outlier_mask(noc, depth, mask, bbox_xy0, kinv=None, source: str 
     return out
 
 
-def _forward_outputs(ctx, noc, depth, mask, bbox_xy0, kinv, sample_idx, ratio_adapt, ref_compat):
+def _forward_outputs(ctx, noc, depth, mask, bbox_xy0, kinv, sample_idx, ratio_adapt, ref_compat, return_mask):
     """Shared forward of PoseFit / PoseFitFull.  Everything the operator returns is written by the library's kernels:
     scale / R / t as float32 by the solve kernel, the plain fit's "inlier" mask (every valid correspondence,
     pose_estimation.py:23-25) by the moments kernel -- no eager torch arithmetic on the batch."""
@@ -313,7 +313,7 @@ def _forward_outputs(ctx, noc, depth, mask, bbox_xy0, kinv, sample_idx, ratio_ad
     scale = torch.empty(b, dtype=torch.float32, device=dev)
     rot = torch.empty(b, 3, 3, dtype=torch.float32, device=dev)
     trans = torch.empty(b, 3, dtype=torch.float32, device=dev)
-    valid = torch.empty(b, h, w, dtype=torch.uint8, device=dev) if sample_idx is None else None
+    valid = torch.empty(b, h, w, dtype=torch.uint8, device=dev) if (sample_idx is None and return_mask) else None
     raw = pose_fit_raw(noc, depth, mask, bbox_xy0, kinv, sample_idx, ratio_adapt, ref_compat, _f32=(scale, rot, trans),
                        _valid_mask=valid)
     inl = raw.inlier_mask if raw.inlier_mask is not None else valid
@@ -321,7 +321,8 @@ def _forward_outputs(ctx, noc, depth, mask, bbox_xy0, kinv, sample_idx, ratio_ad
     ctx.kinv = kinv
     ctx.depth_grad = bool(depth.requires_grad)
     ctx.in_dtypes = (noc.dtype, depth.dtype)
-    ctx.save_for_backward(noc, depth, mask, bbox_xy0, raw.ctx, raw.status, inl)
+    ctx.save_for_backward(noc, depth, mask, bbox_xy0, raw.ctx, raw.status,
+                          raw.inlier_mask if raw.inlier_mask is not None else torch.empty(0, dtype=torch.uint8, device=dev))
     out_dtype = noc.dtype if noc.dtype.is_floating_point else torch.float32
     if out_dtype != torch.float32:
         scale, rot, trans = scale.to(out_dtype), rot.to(out_dtype), trans.to(out_dtype)
@@ -330,7 +331,11 @@ def _forward_outputs(ctx, noc, depth, mask, bbox_xy0, kinv, sample_idx, ratio_ad
 
 class PoseFit(torch.autograd.Function):
     """(scale[B], R[B,3,3], t[B,3], inlier_mask[B,H,W] u8, status[B] i32, n_valid[B] i32) =
-    PoseFit.apply(noc, depth, mask, bbox_xy0, kinv, sample_idx, ratio_adapt, ref_compat).
+    PoseFit.apply(noc, depth, mask, bbox_xy0, kinv, sample_idx, ratio_adapt, ref_compat, return_mask).
+
+    inlier_mask: the RANSAC winner's inlier set.  For the plain fit (sample_idx=None) every valid correspondence takes
+    part (mask != 0 and depth > 0, pose_estimation.py:23-25); that mask is only materialised -- by the moments kernel,
+    1 B/pixel of extra traffic -- when return_mask=True, otherwise the slot is None.
 
     R is the true rotation (the reference's `Rotation` is R^T, pose_utils.py:44), so the
     object-to-camera matrix of run_pose (pose_estimation.py:401-403) is [s*R | t].  Outputs have
@@ -338,10 +343,11 @@ class PoseFit(torch.autograd.Function):
     and, if it requires grad, to `depth`; the RANSAC selection is a constant."""
 
     @staticmethod
-    def forward(ctx, noc, depth, mask, bbox_xy0, kinv=None, sample_idx=None, ratio_adapt=1.0, ref_compat=True):
+    def forward(ctx, noc, depth, mask, bbox_xy0, kinv=None, sample_idx=None, ratio_adapt=1.0, ref_compat=True,
+                return_mask=False):
         scale, rot, trans, inl, raw = _forward_outputs(ctx, noc, depth, mask, bbox_xy0, kinv, sample_idx, ratio_adapt,
-                                                       ref_compat)
-        ctx.mark_non_differentiable(inl, raw.status, raw.n_valid)
+                                                       ref_compat, return_mask)
+        ctx.mark_non_differentiable(*[t for t in (inl, raw.status, raw.n_valid) if t is not None])
         return scale, rot, trans, inl, raw.status, raw.n_valid
 
     @staticmethod
@@ -352,13 +358,13 @@ class PoseFit(torch.autograd.Function):
         g_noc = g_noc.to(ctx.in_dtypes[0])
         if g_depth is not None:
             g_depth = g_depth.to(ctx.in_dtypes[1])
-        return g_noc, g_depth, None, None, None, None, None, None
+        return g_noc, g_depth, None, None, None, None, None, None, None
 
 
 def pose_fit(noc, depth, mask, bbox_xy0, kinv=None, sample_idx=None, ratio_adapt: float = 1.0,
-             ref_compat: bool = True):
+             ref_compat: bool = True, return_mask: bool = False):
     """Keyword-friendly PoseFit.apply."""
-    return PoseFit.apply(noc, depth, mask, bbox_xy0, kinv, sample_idx, ratio_adapt, ref_compat)
+    return PoseFit.apply(noc, depth, mask, bbox_xy0, kinv, sample_idx, ratio_adapt, ref_compat, return_mask)
 
 
 class PoseFitFull(torch.autograd.Function):
@@ -367,11 +373,12 @@ class PoseFitFull(torch.autograd.Function):
     Returns (scale, R, t, inlier_mask, status, n_valid, pose64 [B,16], winner [B] or empty)."""
 
     @staticmethod
-    def forward(ctx, noc, depth, mask, bbox_xy0, kinv=None, sample_idx=None, ratio_adapt=1.0, ref_compat=True):
+    def forward(ctx, noc, depth, mask, bbox_xy0, kinv=None, sample_idx=None, ratio_adapt=1.0, ref_compat=True,
+                return_mask=False):
         scale, rot, trans, inl, raw = _forward_outputs(ctx, noc, depth, mask, bbox_xy0, kinv, sample_idx, ratio_adapt,
-                                                       ref_compat)
+                                                       ref_compat, return_mask)
         winner = raw.winner if raw.winner is not None else torch.empty(0, dtype=torch.int32, device=noc.device)
-        ctx.mark_non_differentiable(inl, raw.status, raw.n_valid, raw.pose, winner)
+        ctx.mark_non_differentiable(*[t for t in (inl, raw.status, raw.n_valid, raw.pose, winner) if t is not None])
         return scale, rot, trans, inl, raw.status, raw.n_valid, raw.pose, winner
 
     @staticmethod

@@ -92,13 +92,19 @@ def bind_host_to_gpu(device_index: int, sysfs: str = '/sys') -> Optional[int]:
 class PeerPoseGather:
     """All-gather of the pose records over NVLink peer memory, moved by the copy engines.
 
-    Every rank owns a [world * n_local, width] buffer in symmetric memory (torch.distributed._symmetric_memory:
-    each buffer is mapped into every peer's address space).  `start(local)` queues, on a side stream and behind
-    the work already on the current stream, one device-to-device copy of this rank's records into its slot of
-    EVERY rank's buffer, then a signal-pad barrier; `wait()` makes the current stream wait for that barrier and
-    returns the gathered tensor.  No SM is occupied by the transfer, so unlike an NCCL all-gather it can run
-    beside an HBM-bound kernel without displacing its CTAs.  The caller must not `start` the next gather while
-    a peer may still be reading the previous result (one step of slack is enough in a training loop).
+    Every rank owns TWO [world * n_local, width] buffers in symmetric memory (torch.distributed._symmetric_memory:
+    each buffer is mapped into every peer's address space), used alternately.  `start(local)` queues, on a side
+    stream and behind the work already on the current stream, one device-to-device copy of this rank's records into
+    its slot of EVERY rank's buffer for this step, then a signal-pad barrier; `wait()` makes the current stream wait
+    for that barrier and returns the gathered tensor.  No SM is occupied by the transfer, so unlike an NCCL all-gather
+    it can run beside an HBM-bound kernel without displacing its CTAs.
+
+    Why two buffers: with one, a fast rank's copies for step n+1 could land in a slower peer's buffer while that
+    peer's kernels still read step n's records.  With two, step n+1 writes the OTHER buffer; step n+2 reuses step n's,
+    and by then the barrier of step n+1 has passed -- every rank's step-(n+1) copies, which that rank's side stream
+    ordered behind everything its compute stream had queued (its readers of step n included), are complete.  So the
+    tensor returned by `wait()` stays valid until the caller's `start()` two steps later, provided its readers were
+    queued on the current stream before the next `start()`.
     Construction is collective; it raises if symmetric memory is not available (callers fall back to
     `gather_poses`, the NCCL path)."""
 
@@ -110,9 +116,16 @@ class PeerPoseGather:
         self.n = int(n_local)
         self.timeout_ms = int(timeout_ms)
         dev = torch.device('cuda', torch.cuda.current_device())
-        self.buf = symm.empty(self.world * self.n, width, dtype=dtype, device=dev)
-        self.hdl = symm.rendezvous(self.buf, self.group)
-        self.peers = [self.hdl.get_buffer(r, (self.world * self.n, width), dtype) for r in range(self.world)]
+        self.bufs, self.hdls, self.peers = [], [], []
+        for _ in range(2):
+            buf = symm.empty(self.world * self.n, width, dtype=dtype, device=dev)
+            hdl = symm.rendezvous(buf, self.group)
+            self.bufs.append(buf)
+            self.hdls.append(hdl)
+            self.peers.append([hdl.get_buffer(r, (self.world * self.n, width), dtype) for r in range(self.world)])
+        self.buf = self.bufs[0]                                  # (shape / dtype reference)
+        self.step = 0
+        self.cur = 0
         self.stream = torch.cuda.Stream()
         self.done = torch.cuda.Event()
 
@@ -120,16 +133,19 @@ class PeerPoseGather:
         if tuple(local.shape) != (self.n, self.buf.shape[1]) or local.dtype != self.buf.dtype:
             raise ValueError('local records do not match the gather buffer')
         local = local.contiguous()
+        self.cur = self.step & 1
+        self.step += 1
+        peers, hdl = self.peers[self.cur], self.hdls[self.cur]
         self.stream.wait_stream(torch.cuda.current_stream())
         lo = self.rank * self.n
         with torch.cuda.stream(self.stream):
             local.record_stream(self.stream)
             for k in range(self.world):
                 r = (self.rank + k) % self.world                 # every rank starts with a different target
-                self.peers[r][lo:lo + self.n].copy_(local, non_blocking=True)
-            self.hdl.barrier(channel=0, timeout_ms=self.timeout_ms)   # all ranks' copies have landed
+                peers[r][lo:lo + self.n].copy_(local, non_blocking=True)
+            hdl.barrier(channel=0, timeout_ms=self.timeout_ms)   # all ranks' copies of this step have landed
             self.done.record(self.stream)
 
     def wait(self) -> torch.Tensor:
         torch.cuda.current_stream().wait_event(self.done)
-        return self.buf
+        return self.bufs[self.cur]

@@ -648,12 +648,12 @@ def run_ours(args):
         torch.cuda.synchronize()
         ms_api = a0.elapsed_time(a1) / k_api
         d['noc'].requires_grad_(False)
-        b_api = n_obj * (18 * P + 64) + bytes_bwd               # + 1 B/px: the validity mask the operator returns
+        b_api = bytes_fwd + bytes_bwd
         configs['C5 shard via PoseFit.apply + backward'] = {
             'ms': ms_api, 'objects_per_s': n_obj / ms_api * 1e3, 'gbs': b_api / ms_api / 1e6,
             'frac': b_api / ms_api / 1e6 / hbm_peak, 'vs_raw_api': ms_api / ms,
-            'note': 'public torch.autograd.Function (pose_fit, kinv=None) + backward, eager launches; algorithmic bytes '
-                    'include the 1 B/px validity mask the operator returns'}
+            'note': 'public torch.autograd.Function (pose_fit, kinv=None) + autograd backward, eager launches; scale / R / t '
+                    'are written as float32 by the solve kernel (no eager torch arithmetic on the batch)'}
 
         # ---- config 5 as written: 1,000,000 objects on ONE GPU (69.6 GB of inputs + 49 GB of NOC gradient)
         if world == 1 and not args.no_full and n_obj < TOTAL_OBJECTS:

@@ -14,6 +14,21 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.fixture(scope='module')
+
+def _golden_aabb_permutation():
+    """Row permutation sort_bbox (the reference's own, pose_estimation.py:72-93) applies to the 8 corners of an
+    axis-aligned box with positive extent on every axis, read off the golden vectors of the real function."""
+    import os
+    from conftest import GOLDEN
+    g = np.load(os.path.join(GOLDEN, 'sort_bbox.npz'))
+    perms = []
+    for k in range(int(g['n'])):
+        if str(g[f'tag_{k}']) == 'aabb extent mask 7':
+            src, dst = g[f'in_{k}'], g[f'out_{k}']
+            perms.append([int(np.where((src == row).all(axis=1))[0][0]) for row in dst])
+    assert len(perms) >= 4 and all(p == perms[0] for p in perms)
+    return perms[0]
+
 def pf():
     if not torch.cuda.is_available():
         pytest.skip('no CUDA device')
@@ -222,8 +237,11 @@ def test_batched_epilogue(pf):
         fm[y0:y0 + h, x0:x0 + w] = d['mask'][i].numpy() != 0
         pts, _ = po.backproject_points(fd.astype(np.float64), po.motfront_intrinsics(), fm)
         world = po.camera_to_world(pts, cp)
-        box = pf.pose_estimation.sort_bbox(pf.pose_estimation._aabb_corners(world))
+        # corner order: the permutation the REAL sort_bbox applies to a generic axis-aligned box (tests/golden/sort_bbox.npz,
+        # oracle/gen_golden_bbox.py); the order Open3D's get_box_points() hands it the corners in stays unpinned
+        box = pf.pose_estimation._aabb_corners(world)[_golden_aabb_permutation()]
         np.testing.assert_allclose(epi.world_box[i].cpu().numpy(), box, rtol=1e-12, atol=1e-12)
+        np.testing.assert_array_equal(box, pf.pose_estimation.sort_bbox(pf.pose_estimation._aabb_corners(world)))
     # camera-space variant (run_pose_office)
     epi2 = pf.pose_epilogue(raw, t['depth'], t['mask'], t['bbox_xy0'])
     i = 0

@@ -548,7 +548,7 @@ def test_backward_vs_autograd_oracle(pf, h, w, with_ransac):
     t = _cuda(d)
     noc = t['noc'].clone().requires_grad_(True)
     depth = t['depth'].clone().requires_grad_(True)
-    out = pf.pose_fit(noc, depth, t['mask'], t['bbox_xy0'], sample_idx=t.get('sample_idx'))
+    out = pf.pose_fit(noc, depth, t['mask'], t['bbox_xy0'], sample_idx=t.get('sample_idx'), return_mask=True)
     scale, rot, trans, inl, status, n_valid = out
     gen = torch.Generator().manual_seed(7)
     g_s = torch.randn(b, generator=gen)
@@ -697,7 +697,8 @@ def test_public_operator_capturable_with_default_intrinsics(pf):
 
     def work(idx):
         noc = d['noc'].detach().clone().requires_grad_(True)
-        scale, rot, trans, inl, status, n_valid = pf.pose_fit(noc, d['depth'], d['mask'], d['bbox_xy0'], sample_idx=idx)
+        scale, rot, trans, inl, status, n_valid = pf.pose_fit(noc, d['depth'], d['mask'], d['bbox_xy0'], sample_idx=idx,
+                                                              return_mask=True)
         ((scale * g[0]).sum() + (rot * g[1]).sum() + (trans * g[2]).sum()).backward()
         return scale, rot, trans, inl, noc.grad
 
@@ -727,7 +728,8 @@ def test_public_operator_capturable_with_default_intrinsics(pf):
         assert torch.equal(eager[3], want)
     # ragged shape / unaligned views take the generic loaders: the validity mask is still the kernel's
     d3 = pf.synth.make_objects(5, 19, 27, seed=92, device='cuda', align_x0=1)
-    out = pf.pose_fit(d3['noc'], d3['depth'], d3['mask'], d3['bbox_xy0'])
+    out = pf.pose_fit(d3['noc'], d3['depth'], d3['mask'], d3['bbox_xy0'], return_mask=True)
+    assert pf.pose_fit(d3['noc'], d3['depth'], d3['mask'], d3['bbox_xy0'])[3] is None     # opt-in for the plain fit
     assert torch.equal(out[3], ((d3['mask'] != 0) & (d3['depth'] > 0)).to(torch.uint8))
 
 

@@ -142,3 +142,17 @@ def test_clip_to_box_matches_reference(golden_dir):
         np.testing.assert_array_equal(g[f'pts_{k}'][keep].reshape(-1, 3), g[f'new_depth_{k}'])
         sizes.append(len(keep))
     assert min(sizes) <= 20 < max(sizes)          # both sides of run_pose's "> 20" rule are covered
+
+
+def test_sort_bbox_matches_reference(golden_dir):
+    """sort_bbox (pose_estimation.py:72-93): the product's drop-in and the oracle's restatement against what the REAL
+    function returned (oracle/gen_golden_bbox.py) -- axis-aligned boxes in the epilogue's corner order for every
+    zero / positive extent pattern (argsort ties), shuffled corners, arbitrary and repeated points."""
+    import importlib
+    drop_in = importlib.import_module('3d_mot_differentiable_pose_estimation_b200.pose_estimation')
+    g = np.load(os.path.join(golden_dir, 'sort_bbox.npz'))
+    n = int(g['n'])
+    assert n >= 100
+    for k in range(n):
+        got = drop_in.sort_bbox(g[f'in_{k}'].copy())
+        np.testing.assert_array_equal(got, g[f'out_{k}'], err_msg=str(g[f'tag_{k}']))

@@ -24,6 +24,27 @@ for it in range(3):
     torch.cuda.synchronize()
     assert torch.equal(got, want), (rank, it)
     dist.barrier()
+# Skewed ranks, the gathered tensor READ on every step by a slow consumer kernel that is still running when a faster
+# peer has already started the next step's copies: with the two alternating buffers no step may see another step's records.
+torch.cuda.synchronize(); dist.barrier()
+checks = []
+for it in range(12):
+    local = torch.full((n, 16), float(1000 * it + rank), dtype=torch.float64, device='cuda')
+    if it % world == rank:
+        torch.cuda._sleep(20_000_000)                            # ~10 ms: this rank lags behind its peers
+    pg.start(local)
+    got = pg.wait()
+    acc = torch.zeros(world, dtype=torch.float64, device='cuda')
+    for rep in range(4 if (it + 1) % world == rank else 1):      # a slow reader of THIS step's records
+        acc = acc + got.view(world, n * 16).double().mean(dim=1) / (4 if (it + 1) % world == rank else 1)
+    checks.append((it, acc))
+torch.cuda.synchronize()
+for it, acc in checks:
+    want = torch.tensor([1000.0 * it + r for r in range(world)], dtype=torch.float64, device='cuda')
+    assert torch.allclose(acc, want, rtol=0, atol=1e-9), (rank, it, acc.tolist(), want.tolist())
+dist.barrier()
+if rank == 0:
+    print('peer gather: 12 skewed steps read back correctly on every rank')
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
 torch.cuda.synchronize(); dist.barrier()
 ev[0].record()
