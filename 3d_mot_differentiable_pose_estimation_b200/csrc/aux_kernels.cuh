@@ -698,7 +698,12 @@ __global__ void __launch_bounds__(256) gather_crops_kernel(const GatherParams p)
   int x0 = p.bbox_xyxy[4 * obj], y0 = p.bbox_xyxy[4 * obj + 1], x1 = p.bbox_xyxy[4 * obj + 2], y1 = p.bbox_xyxy[4 * obj + 3];
   x0 = max(0, min(x0, p.FW)); x1 = max(x0, min(x1, p.FW));
   y0 = max(0, min(y0, p.FH)); y1 = max(y0, min(y1, p.FH));
-  const int h = min(y1 - y0, p.H), w = min(x1 - x0, p.W);
+  // A box larger than the canvas cannot be represented (cropping depth / mask while the NOC patch is resized to the
+  // truncated size would pair the wrong pixels): such an instance is emitted EMPTY (no valid pixel -> status 1, the
+  // reference's "no correspondences" answer) instead of silently wrong.  Callers that hold the boxes on the host
+  // are told up front (frontend.run_pose_batched raises).
+  const bool fits = (y1 - y0) <= p.H && (x1 - x0) <= p.W;
+  const int h = fits ? y1 - y0 : 0, w = fits ? x1 - x0 : 0;
   if (tid == 0) {
     p.bbox_xy0[2 * obj] = x0; p.bbox_xy0[2 * obj + 1] = y0;
     p.roi_hw[2 * obj] = h;    p.roi_hw[2 * obj + 1] = w;

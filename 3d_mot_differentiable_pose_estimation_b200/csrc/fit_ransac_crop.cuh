@@ -144,10 +144,10 @@ __device__ __forceinline__ void crop_pass1(const FwdParams& p, const unsigned ch
 
 // lane j: pixel of sample j of the hypothesis whose indices start at gidx_h (pose_utils.py:73), into spx[j]
 __device__ __forceinline__ void crop_sample_pixels(const uint16_t* klist, const uint32_t* bits, const int32_t* gidx_h,
-                                                   int n_samp, int N, uint16_t* spx) {
+                                                   int n_samp, int N, int idx_bits, uint16_t* spx) {
   const int lane = threadIdx.x & 31;
   if (lane < n_samp) {
-    const int k = max(0, min(__ldg(gidx_h + lane), N - 1));
+    const int k = sample_index(__ldg(gidx_h + lane), N, idx_bits);
     spx[lane] = (uint16_t)select_px_list(klist, bits, k);
   }
   __syncwarp();
@@ -569,7 +569,7 @@ __global__ void __launch_bounds__(NT, 3) fit_ransac_crop_kernel(const FwdParams 
         int k_next = __ldg(gi);
 #pragma unroll 1
         for (int j = 0; j < p.n_samp; ++j) {
-          const int k = max(0, min(k_next, N - 1));                        // pose_utils.py:73
+          const int k = sample_index(k_next, N, p.idx_bits);              // pose_utils.py:73
           if (j + 1 < p.n_samp) k_next = __ldg(gi + j + 1);
           const int px = select_px_list(klist, bits, k);
           const int row = (int)__umulhi((uint32_t)px, p.w_magic), col = px - row * p.W;
@@ -662,7 +662,7 @@ __global__ void __launch_bounds__(NT, 3) fit_ransac_crop_kernel(const FwdParams 
       float_pass = sh->band_rel < 0.05f;                          // an unusable / sloppy float fit: take the exact path
       // the winner's sample pixels, resolved now: the inlier pass reuses the select list's memory for its queues
       if (warp == 0) {
-        crop_sample_pixels(klist, bits, gidx + win * p.n_samp, p.n_samp, N, sh->spx[0]);
+        crop_sample_pixels(klist, bits, gidx + win * p.n_samp, p.n_samp, N, p.idx_bits, sh->spx[0]);
         if (!float_pass)
           crop_fit_hypothesis(snoc, sdep, rxc, ryr, sh->spx[0], sh, red, sh->wtf, p.n_samp, P, p.W, p.w_magic, p.ref_compat);
       }
@@ -692,7 +692,7 @@ __global__ void __launch_bounds__(NT, 3) fit_ransac_crop_kernel(const FwdParams 
             sh->start[warp][9] = (have32 && p.n_hyp <= NT) ? 1.0f : 0.0f;
           }
           __syncwarp();
-          crop_sample_pixels(klist, bits, gidx + hc * p.n_samp, p.n_samp, N, sh->spx[warp]);
+          crop_sample_pixels(klist, bits, gidx + hc * p.n_samp, p.n_samp, N, p.idx_bits, sh->spx[warp]);
           const double r2 = crop_fit_hypothesis(snoc, sdep, rxc, ryr, sh->spx[warp], sh, red + warp * 24, cur + warp * 12,
                                                 p.n_samp, P, p.W, p.w_magic, p.ref_compat);
           // keep the transform of this warp's leading hypothesis

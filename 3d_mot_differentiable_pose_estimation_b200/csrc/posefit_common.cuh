@@ -82,6 +82,7 @@ struct FwdParams {
   int kinv_per_object;
   int B, H, W, P;
   int n_hyp, n_samp, ref_compat;
+  int idx_bits;                 // sample_idx holds uniform 32-bit values (device-side draws), mapped to floor(u N / 2^32)
   int no_fast;                  // debugging: force the generic per-pixel passes of the RANSAC kernel
   int no_idx_preload;           // debugging: per-sample index loads in the RANSAC gather loop
   int no_early_issue;           // debugging: request every crop at the top of its own iteration
@@ -127,6 +128,13 @@ __device__ __forceinline__ void cp_async_4(void* dst, const void* src) {
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// Sample index of a RANSAC hypothesis (pose_utils.py:73) from the caller's tensor: an index into the compacted
+// correspondences, clamped into [0, N) -- or, with idx_bits, a uniform 32-bit value u mapped to floor(u N / 2^32)
+// (draws made on the device before N is known: include/posefit.h, POSEFIT_SAMPLES_ARE_BITS).
+__device__ __forceinline__ int sample_index(int raw, int N, int idx_bits) {
+  return idx_bits ? (int)__umulhi((uint32_t)raw, (uint32_t)N) : max(0, min(raw, N - 1));
+}
 
 // threads 0..10 request the geometry record of `obj` into `dst`
 __device__ __forceinline__ void fetch_geom(const FwdParams& p, int obj, GeomSmem* dst, int tid) {

@@ -136,11 +136,12 @@ def _draw_sample_idx(counts, n_iterations: int, n_samples: int) -> torch.Tensor:
     return torch.from_numpy(idx)
 
 
-def _fit(noc, crops, mask, kinv, campose, cam_index, sample_idx, ransac):
-    from .function import PoseFitFull, PoseFitRaw, pose_epilogue
+def _fit(noc, crops, mask, kinv, campose, cam_index, sample_idx, ransac, bits=False):
+    from .function import PoseFitFull, PoseFitRaw, pose_epilogue, REF_COMPAT, SAMPLES_ARE_BITS
     # one forward feeds both autograd (the reference detaches here, postprocess.py:151; we do not have to) and the epilogue
     scale, rot, trans, inl, status, n_valid, pose64, winner = PoseFitFull.apply(
-        noc, crops.depth, mask, crops.bbox_xy0, kinv, sample_idx if ransac else None, 1.0, True)
+        noc, crops.depth, mask, crops.bbox_xy0, kinv, sample_idx if ransac else None, 1.0,
+        REF_COMPAT | (SAMPLES_ARE_BITS if bits else 0))
     raw = PoseFitRaw(pose64, None, status, n_valid, inl if ransac else None, winner if ransac else None)
     epi = pose_epilogue(raw, crops.depth, mask, crops.bbox_xy0, kinv, campose=campose, cam_index=cam_index)
     return BatchedPoses(epi.global_rot, epi.global_trans, epi.global_scale, epi.euler, epi.world_box, status,
@@ -157,7 +158,7 @@ def run_pose_batched(pred_nocs, depth_frames, inst_masks, boxes_xyxy, frame_of: 
                      campose=None, kinv=None, gt_boxes=None, ransac: bool = True, n_iterations: int = 100,
                      n_samples: int = 10, apply_statistical_filter: bool = True, sample_idx=None,
                      height: Optional[int] = None, width: Optional[int] = None,
-                     bucket: Optional[int] = None) -> BatchedPoses:
+                     bucket: Optional[int] = None, generator=None) -> BatchedPoses:
     """The per-instance loop of `postprocess_dets` (Detection/tracker/postprocess.py:131-165) -- roi_align of
     the NOC head output, depth / mask slicing, run_pose -- for ALL instances of a batch of frames at once.
 
@@ -167,7 +168,13 @@ def run_pose_batched(pred_nocs, depth_frames, inst_masks, boxes_xyxy, frame_of: 
     RANSAC indices are drawn from the global `np.random` stream exactly as the per-instance drop-in does
     (instance after instance, `randint(N_i, size=(n_iterations, n_samples))`, nothing for an empty instance)
     unless `sample_idx` [B,n_hyp,n_samp] is given; the only host round trip is the B correspondence counts
-    that `randint` needs.  Instances are padded to one H x W (default: the largest box, width rounded up to 4).
+    that `randint` needs.  sample_idx='device' removes that round trip too: the draws are made on the GPU (torch's
+    Philox generator, `generator=`) as uniform 32-bit values that the kernels map to floor(u N / 2^32) once they know N
+    -- an opt-in, NOT numpy's stream.  Early stop and the global stream: the reference draws 10 indices per iteration
+    and stops drawing at its early-stop break (pose_utils.py:73-81), while this function (like the per-instance drop-ins)
+    draws all n_iterations x n_samples up front; after an early stop -- total residual below PassT / 100, i.e. a
+    near-perfect object -- the global np.random stream is therefore ahead of where the reference would leave it.
+    Instances are padded to one H x W (default: the largest box, width rounded up to 4).
 
     bucket=k: boxes of very different sizes make that padding the dominant traffic (a 24x24 box on a 160x200 canvas
     reads 55x its own bytes).  With `bucket` the instances are grouped by box size rounded up to multiples of k and
@@ -177,16 +184,28 @@ def run_pose_batched(pred_nocs, depth_frames, inst_masks, boxes_xyxy, frame_of: 
     boxes = torch.as_tensor(boxes_xyxy)
     if bucket and int(boxes.shape[0]) > 0:
         return _run_pose_bucketed(pred_nocs, depth_frames, inst_masks, boxes, frame_of, campose, kinv, gt_boxes, ransac,
-                                  n_iterations, n_samples, apply_statistical_filter, sample_idx, int(bucket))
+                                  n_iterations, n_samples, apply_statistical_filter, sample_idx, int(bucket), generator)
     if height is None or width is None:
         ch, cw = _canvas(boxes)
         height, width = height or ch, width or cw
+    elif not boxes.is_cuda and boxes.numel():
+        # explicit canvas + boxes on the host: check here (device-resident boxes are checked by the gather kernel, which
+        # emits an instance whose box exceeds the canvas as EMPTY -- status 1 -- rather than cropping it)
+        bh, bw = int((boxes[:, 3] - boxes[:, 1]).max()), int((boxes[:, 2] - boxes[:, 0]).max())
+        if bh > height or bw > width:
+            raise ValueError(f'canvas {height}x{width} is smaller than the largest box ({bh}x{bw})')
     crops, noc, mask, cam_index = _prepare(pred_nocs, depth_frames, inst_masks, boxes, frame_of, campose, kinv, gt_boxes,
                                            apply_statistical_filter, height, width)
+    bits = isinstance(sample_idx, str)
+    if bits:
+        if sample_idx != 'device':
+            raise ValueError("sample_idx must be a tensor, None or 'device'")
+        from .function import device_sample_bits
+        sample_idx = device_sample_bits(int(mask.shape[0]), n_iterations, n_samples, mask.device, generator)
     if ransac and sample_idx is None:
         counts = ((mask != 0) & (crops.depth > 0)).flatten(1).sum(1).cpu().numpy()     # the one host round trip
         sample_idx = _draw_sample_idx(counts, n_iterations, n_samples)
-    return _fit(noc, crops, mask, kinv, campose, cam_index, sample_idx, ransac)
+    return _fit(noc, crops, mask, kinv, campose, cam_index, sample_idx, ransac, bits)
 
 
 def bucket_groups(boxes_xyxy, bucket: int) -> dict:
@@ -203,8 +222,15 @@ def bucket_groups(boxes_xyxy, bucket: int) -> dict:
 
 
 def _run_pose_bucketed(pred_nocs, depth_frames, inst_masks, boxes, frame_of, campose, kinv, gt_boxes, ransac,
-                       n_iterations, n_samples, apply_statistical_filter, sample_idx, bucket: int) -> BatchedPoses:
+                       n_iterations, n_samples, apply_statistical_filter, sample_idx, bucket: int,
+                       generator=None) -> BatchedPoses:
     b = int(boxes.shape[0])
+    bits = isinstance(sample_idx, str)
+    if bits:
+        if sample_idx != 'device':
+            raise ValueError("sample_idx must be a tensor, None or 'device'")
+        from .function import device_sample_bits
+        sample_idx = device_sample_bits(b, n_iterations, n_samples, pred_nocs.device, generator)
     groups = bucket_groups(boxes, bucket)
     dev = pred_nocs.device
 
@@ -227,7 +253,7 @@ def _run_pose_bucketed(pred_nocs, depth_frames, inst_masks, boxes, frame_of, cam
         sample_idx = _draw_sample_idx(counts.cpu().numpy(), n_iterations, n_samples)     # the one host round trip
     if sample_idx is not None:
         sample_idx = torch.as_tensor(sample_idx).to(dev)
-    parts = [_fit(noc, crops, mask, k_g, campose, cam_index, sample_idx[idx] if ransac else None, ransac)
+    parts = [_fit(noc, crops, mask, k_g, campose, cam_index, sample_idx[idx] if ransac else None, ransac, bits)
              for idx, k_g, crops, noc, mask, cam_index in prepared]
     order = torch.cat([pr[0] for pr in prepared]) if prepared else torch.zeros(0, dtype=torch.long, device=dev)
     inv = torch.argsort(order)

@@ -24,6 +24,9 @@ import torch
 from . import _lib
 
 STATUS_OK, STATUS_EMPTY, STATUS_LOW_INLIER_RATIO, STATUS_NAN = 0, 1, 2, 3
+# flag bits of `ref_compat` (include/posefit.h): True / 1 = the reference's scoring quirks; | SAMPLES_ARE_BITS = sample_idx
+# holds uniform 32-bit draws that the kernel maps to floor(u * N / 2^32) (see device_sample_bits)
+REF_COMPAT, SAMPLES_ARE_BITS = 1, 2
 
 
 class PoseFitRaw(NamedTuple):
@@ -133,11 +136,19 @@ def pose_fit_raw(noc, depth, mask, bbox_xy0, kinv=None, sample_idx=None, ratio_a
         ws = _workspace(lib, dev, b, h, w, max(n_hyp, 1), n_samp)
         code = lib.posefit_forward_ransac_ex(_ptr(noc), _ptr(depth), _ptr(mask), _ptr(bbox_xy0), _ptr(kinv), per_obj,
                                              _ptr(sample_idx), b, h, w, n_hyp, n_samp, float(ratio_adapt),
-                                             int(bool(ref_compat)), _ptr(pose), _ptr(ctx), _ptr(status),
+                                             int(ref_compat), _ptr(pose), _ptr(ctx), _ptr(status),
                                              _ptr(n_valid), _ptr(inl), _ptr(winner), _ptr(fs), _ptr(fr), _ptr(ft),
                                              _ptr(ws), ws.numel(), _stream(dev))
         _lib.check(code, 'posefit_forward_ransac')
     return PoseFitRaw(pose, ctx, status, n_valid, inl, winner)
+
+
+def device_sample_bits(n_objects: int, n_hyp: int, n_samp: int = 10, device='cuda', generator=None) -> torch.Tensor:
+    """RANSAC draws made ON THE DEVICE (torch's Philox generator), before anyone knows how many correspondences an
+    object has: uniform 32-bit values u, which the kernels map to floor(u * N / 2^32) when `ref_compat` carries
+    SAMPLES_ARE_BITS.  Not numpy's stream -- host-supplied indices remain the parity mode (pose_utils.py:73)."""
+    u = torch.randint(-2 ** 31, 2 ** 31, (n_objects, n_hyp, n_samp), dtype=torch.int64, device=device, generator=generator)
+    return u.to(torch.int32)
 
 
 def points_fit_raw(src, dst, mask=None, sample_idx=None, ratio_adapt: float = 1.0,

@@ -53,6 +53,11 @@ extern "C" {
 #define POSEFIT_E_WORKSPACE (-3)  /* workspace too small */
 #define POSEFIT_E_SMEM (-4)       /* crop does not fit the shared-memory staging of the RANSAC path */
 
+/* Flag bits of the RANSAC entries' `ref_compat` argument. */
+#define POSEFIT_REF_COMPAT 1          /* reproduce the reference's scoring quirks (see posefit_forward_ransac) */
+#define POSEFIT_SAMPLES_ARE_BITS 2    /* sample_idx holds uniform 32-bit values u (drawn on the device, before the number of
+                                         correspondences N is known); hypothesis sample = floor(u * N / 2^32) */
+
 /* ABI version of the loaded library. */
 int posefit_version(void);
 
@@ -81,9 +86,10 @@ int posefit_forward(const float* noc, const float* depth, const uint8_t* mask, c
  * np.random.randint at :73; values >= n_valid[b] are clamped), scored as evaluateModel does
  * (:5-14), first-minimum selection with early stop (:76-81), the ratio gate (:105-107) and the
  * refit on the winner's inliers (:109).
- * ref_compat != 0 reproduces the reference exactly: hypotheses are scored with the transposed
- * rotation block the reference builds (:58) and point 0 is never counted as an inlier (:11);
- * ref_compat == 0 scores with s*R and counts every inlier.
+ * ref_compat bit 0 (POSEFIT_REF_COMPAT) set reproduces the reference exactly: hypotheses are scored with the
+ * transposed rotation block the reference builds (:58) and point 0 is never counted as an inlier (:11);
+ * clear: scores with s*R and counts every inlier.  Bit 1 (POSEFIT_SAMPLES_ARE_BITS): sample_idx holds uniform
+ * 32-bit values instead of indices (device-side draws: no host round trip for the correspondence counts).
  * inlier_mask[b][H][W] (uint8) receives the winner's inlier set (all valid pixels when no
  * hypothesis was accepted); winner[b] (optional, may be NULL) the winning hypothesis or -1. */
 int posefit_forward_ransac(const float* noc, const float* depth, const uint8_t* mask, const int32_t* bbox_xy0,

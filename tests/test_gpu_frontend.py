@@ -67,7 +67,9 @@ def test_gather_crops_matches_slicing(pf):
                         torch.from_numpy(frame_of).cuda(), H, W)
     for i in range(b):
         x0, y0, x1, y1 = boxes[i]
-        h, w = min(y1 - y0, H), min(x1 - x0, W)
+        h, w = y1 - y0, x1 - x0
+        if h > H or w > W:
+            h = w = 0            # a box beyond the canvas is emitted EMPTY (never cropped: NOC would be resized to the wrong size)
         assert c.roi_hw[i].cpu().tolist() == [h, w] and c.bbox_xy0[i].cpu().tolist() == [x0, y0]
         want_d = np.zeros((H, W), dtype=np.float32)
         want_m = np.zeros((H, W), dtype=np.uint8)
@@ -75,6 +77,11 @@ def test_gather_crops_matches_slicing(pf):
         want_m[:h, :w] = masks[i, y0:y0 + h, x0:x0 + w]
         np.testing.assert_array_equal(c.depth[i].cpu().numpy(), want_d)
         np.testing.assert_array_equal(c.mask[i].cpu().numpy(), want_m)
+    # with the boxes on the host, run_pose_batched refuses an explicit canvas that is too small
+    with pytest.raises(ValueError):
+        pf.run_pose_batched(torch.rand(b, 3, 28, 28, device='cuda'), torch.from_numpy(depth).cuda(),
+                            torch.from_numpy(masks).cuda(), torch.from_numpy(boxes), torch.from_numpy(frame_of).cuda(),
+                            height=H, width=W, ransac=False, apply_statistical_filter=False)
 
 
 def test_batched_pipeline_equals_per_instance_reference_flow(pf):

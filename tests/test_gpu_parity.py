@@ -733,6 +733,34 @@ def test_public_operator_capturable_with_default_intrinsics(pf):
     assert torch.equal(out[3], ((d3['mask'] != 0) & (d3['depth'] > 0)).to(torch.uint8))
 
 
+def test_device_side_sample_draws(pf, knob):
+    """POSEFIT_SAMPLES_ARE_BITS: sample_idx holds uniform 32-bit draws made on the device; the kernels map u to
+    floor(u N / 2^32).  Same result as host-side indices computed with that formula -- in both RANSAC kernels -- and the
+    oracle agrees on them."""
+    b, n_hyp = 40, 64
+    d = pf.synth.make_objects(b, 64, 64, seed=95, n_hyp=n_hyp)
+    t = _cuda(d)
+    bits = pf.device_sample_bits(b, n_hyp, 10, 'cuda', torch.Generator(device='cuda').manual_seed(3))
+    n = ((t['mask'] != 0) & (t['depth'] > 0)).flatten(1).sum(1).to(torch.int64)
+    u = bits.to(torch.int64) & 0xffffffff
+    idx = ((u * n[:, None, None]) >> 32).to(torch.int32)
+    want = pf.pose_fit_raw(t['noc'], t['depth'], t['mask'], t['bbox_xy0'], sample_idx=idx)
+    got = pf.pose_fit_raw(t['noc'], t['depth'], t['mask'], t['bbox_xy0'], sample_idx=bits,
+                          ref_compat=pf.REF_COMPAT | pf.SAMPLES_ARE_BITS)
+    torch.cuda.synchronize()
+    assert torch.equal(got.inlier_mask, want.inlier_mask) and torch.equal(got.winner, want.winner)
+    assert torch.equal(got.pose, want.pose)
+    knob.set('POSEFIT_RANSAC_SCREEN', '0')                       # the general kernel maps the draws the same way
+    gen = pf.pose_fit_raw(t['noc'], t['depth'], t['mask'], t['bbox_xy0'], sample_idx=bits,
+                          ref_compat=pf.REF_COMPAT | pf.SAMPLES_ARE_BITS)
+    torch.cuda.synchronize()
+    knob.clear('POSEFIT_RANSAC_SCREEN')
+    assert torch.equal(gen.inlier_mask, want.inlier_mask) and torch.equal(gen.winner, want.winner)
+    ora = po.batch_pose(d['noc'].numpy(), d['depth'].numpy(), d['mask'].numpy(), d['bbox_xy0'].numpy(),
+                        sample_idx=idx.cpu().numpy())
+    check_against_oracle(got, ora, ransac=True)
+
+
 def test_full_size_ransac_properties(pf):
     """BASELINE config 3 size (4096 x 64x64, 128 hypotheses): oracle on a 48-object sample, and
     size-independent properties on everything: inliers are a subset of the valid pixels, the
