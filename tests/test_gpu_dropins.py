@@ -14,6 +14,11 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.fixture(scope='module')
+def pf():
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    return load_pkg()
+
 
 def _golden_aabb_permutation():
     """Row permutation sort_bbox (the reference's own, pose_estimation.py:72-93) applies to the 8 corners of an
@@ -28,11 +33,6 @@ def _golden_aabb_permutation():
             perms.append([int(np.where((src == row).all(axis=1))[0][0]) for row in dst])
     assert len(perms) >= 4 and all(p == perms[0] for p in perms)
     return perms[0]
-
-def pf():
-    if not torch.cuda.is_available():
-        pytest.skip('no CUDA device')
-    return load_pkg()
 
 
 def _hom(p):
