@@ -49,6 +49,9 @@ def parse():
     ap.add_argument('--size', type=int, default=64)
     ap.add_argument('--e2e-objects', type=int, default=16384)
     ap.add_argument('--cpu-sample', type=int, default=0, help='objects in the CPU baseline sample (0 = auto)')
+    ap.add_argument('--gather', default='final', choices=['final', 'step'],
+                    help='N > 1: one NCCL all-gather of all pose records after the last step (default, the north star\'s '
+                         '"final gather"), or an all-gather of every step\'s records beside its backward pass')
     ap.add_argument('--no-extra', action='store_true', help='skip the config 2/3/4 side measurements')
     ap.add_argument('--no-full', action='store_true', help='skip the 1M-object single-GPU config-5 measurement (N = 1)')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
@@ -319,7 +322,7 @@ def config_dict(args, n_obj, size):
     return {'workload': workload_name(n_obj, size), 'objects_per_gpu': n_obj, 'crop': [size, size],
             'scaling': args.scaling,
             'l2': 'inputs per step (%.1f GB) exceed the 126 MB L2; no flush needed' % (n_obj * 17 * P / 1e9),
-            'collective': 'all-gather of the 128-B pose records per step (N > 1; none at N = 1)'}
+            'collective': 'NCCL all-gather of the 128-B pose records (N > 1: final or per step, see run.collective; none at N = 1)'}
 
 
 def peaks():
@@ -378,11 +381,16 @@ def run_ours(args):
     g_t = torch.randn(n_obj, 3, device=dev, generator=gen)
     kinv = pf.default_kinv(dev)
 
-    # The one collective: every step all-gathers the 128-byte pose records.  Default: copies over NVLink peer
-    # memory by the copy engines (shard.PeerPoseGather: no SM is taken from the HBM-bound backward kernel it
-    # runs beside); POSEFIT_BENCH_GATHER=sync|async selects the NCCL all_gather after / beside the backward pass,
-    # which is also the fallback when symmetric memory is not available.
-    gather_mode = os.environ.get('POSEFIT_BENCH_GATHER', 'peer') if world > 1 else 'none'
+    # The one collective (north star: "no collective except a final NCCL gather of poses").  --gather final (default):
+    # the steps of the timed region repeat the same job (this rank's shard of the 1M objects); its result -- the pose
+    # records of the shard -- is all-gathered ONCE with NCCL after the last step, INSIDE the timed region.  --gather step: every step all-gathers its 128-byte records -- copies over
+    # NVLink peer memory by the copy engines (shard.PeerPoseGather: no SM is taken from the HBM-bound backward kernel it
+    # runs beside); POSEFIT_BENCH_GATHER=sync|async selects the NCCL all_gather after / beside the backward pass, which is
+    # also the fallback when symmetric memory is not available.
+    gather_mode = 'none'
+    if world > 1:
+        gather_mode = 'final' if args.gather == 'final' else os.environ.get('POSEFIT_BENCH_GATHER', 'peer')
+    kept_poses = []
     peer = None
     if gather_mode == 'peer':
         ok = torch.ones(1, device=dev)
@@ -414,6 +422,8 @@ def run_ours(args):
             work.wait()
         elif gather_mode == 'sync':
             pf.shard.gather_poses(raw.pose)                      # NCCL, after the backward pass, on the same stream
+        elif gather_mode == 'final':
+            kept_poses[:] = [raw.pose]                           # this step's records stay on this GPU
         return [('fit_moments_kernel', e0, e1), ('fit_backward_kernel', e1, e2)]
 
     for attempt in range(2):
@@ -439,9 +449,17 @@ def run_ours(args):
         torch.cuda.synchronize()
         t0, t1 = ev(), ev()
         t0.record()
+        kept_poses.clear()
         recs = [step() for _ in range(args.steps)]
+        gathered = None
+        if gather_mode == 'final':
+            gathered = pf.shard.gather_poses(kept_poses[0])      # the final NCCL gather, inside the timed region
         t1.record()
         torch.cuda.synchronize()
+    if gathered is not None:
+        assert gathered.shape[0] == world * n_obj
+        del gathered
+    kept_poses.clear()
     if world > 1:
         dist.barrier()
     launches = lib.posefit_launch_count() - launches0
@@ -714,6 +732,8 @@ def run_ours(args):
             'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
             'config': config_dict(args, n_obj, size),
             'run': {'collective': {'none': 'none',
+                                   'final': 'one NCCL all_gather of the 128-B pose records (the job\'s result) after the last step, '
+                                            'inside the timed region',
                                    'peer': 'all-gather of 128-B pose records per step over NVLink peer memory '
                                            '(symmetric memory, copy engines) beside the backward pass',
                                    'sync': 'NCCL all_gather of 128-B pose records per step, after the backward pass',
