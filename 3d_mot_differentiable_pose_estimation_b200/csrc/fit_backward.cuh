@@ -176,6 +176,7 @@ __global__ void __launch_bounds__(NT, MINB) fit_backward_kernel(const BwdParams 
     const int ch = unit - obj * p.chunks_per_obj;
     const int px0 = ch * p.chunk_px;
     const int px1 = min(px0 + p.chunk_px, p.P);
+    PF_CHECK(obj >= 0 && obj < p.B && px0 < p.P);
     const size_t ob = (size_t)obj * p.P;
     const float* n0p = p.noc + ob * 3;
     float* g0p = p.grad_noc + ob * 3;

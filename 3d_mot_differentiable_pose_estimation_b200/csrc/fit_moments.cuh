@@ -285,6 +285,7 @@ __global__ void __launch_bounds__(512, 1) fit_moments_kernel(const FwdParams p) 
         col = px0 - row * p.W;
       }
       cp_async_wait_group<DEPTH / 2 - 1>();                     // this lane's copies of both chunks have landed
+      PF_CHECK(slot >= 0 && slot + 1 < DEPTH && obj < p.B && px0 + kChunkPx + 3 < P);
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
         const unsigned char* st = ring + (slot + u) * kChunkBytes + lane * 16;
@@ -394,6 +395,7 @@ __global__ void __launch_bounds__(512, 1) fit_moments_kernel(const FwdParams p) 
       }
     } else {
       cp_async_wait_group<DEPTH - 1>();                       // this lane's copies of this chunk have landed
+      PF_CHECK(slot >= 0 && slot < DEPTH && obj < p.B && (VEC == 2 ? px0 + 3 < P : true));
       const unsigned char* st = ring + slot * kChunkBytes + lane * 16;
       uint32_t m4 = 0u;                                       // 4 mask bytes
       float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -432,6 +434,7 @@ __global__ void __launch_bounds__(512, 1) fit_moments_kernel(const FwdParams p) 
           // lanes past the end of the object (last, partial chunk) carry zeros: keep their table reads
           // inside the tables (with a narrow crop `row` would run far past H, out of the CTA's shared memory)
           const int trow = in_obj ? row : 0, tcol = in_obj ? col : 0;
+          PF_CHECK(trow < p.H && tcol + 3 < p.W);
           const double nry = -ryr[trow];
           const double2 rxa = *reinterpret_cast<const double2*>(rxc + tcol);
           const double2 rxb = *reinterpret_cast<const double2*>(rxc + tcol + 2);

@@ -101,6 +101,8 @@ __device__ __forceinline__ void crop_pass1(const FwdParams& p, const unsigned ch
     v |= __shfl_xor_sync(0xffffffffu, v, 1);
     v |= __shfl_xor_sync(0xffffffffu, v, 2);
     v |= __shfl_xor_sync(0xffffffffu, v, 4);
+    PF_CHECK(!act || (i4 >> 5) < p.n_words);
+    PF_CHECK(row >= 0 && row < p.H && col >= 0 && col + 3 < p.W);
     if ((lane & 7) == 0 && act) bits[i4 >> 5] = v;
     cnt += __popc(nib);
     const double nry = -ryr[row];
@@ -148,7 +150,10 @@ __device__ __forceinline__ void crop_sample_pixels(const uint16_t* klist, const 
   const int lane = threadIdx.x & 31;
   if (lane < n_samp) {
     const int k = sample_index(__ldg(gidx_h + lane), N, idx_bits);
-    spx[lane] = (uint16_t)select_px_list(klist, bits, k);
+    PF_CHECK(k >= 0 && k < N);
+    const int px = select_px_list(klist, bits, k);
+    PF_CHECK(px >= 0 && px < 65536);
+    spx[lane] = (uint16_t)px;
   }
   __syncwarp();
 }
@@ -166,6 +171,7 @@ __device__ __noinline__ double crop_fit_hypothesis(const float* snoc, const floa
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   auto point = [&](int j, double (&xs)[3], double (&ys)[3]) {
     const int px = (int)spx[j];
+    PF_CHECK(px < P);
     const int row = (int)__umulhi((uint32_t)px, w_magic), col = px - row * W;
     const double zd = (double)sdep[px];
     xs[0] = (double)snoc[px] - 0.5; xs[1] = (double)snoc[P + px] - 0.5; xs[2] = (double)snoc[2 * P + px] - 0.5;   // :323
@@ -272,6 +278,7 @@ __device__ __forceinline__ void crop_pass2(const FwdParams& p, const unsigned ch
         uint32_t ent = e < qn ? (uint32_t)q[e] : 0u;
         const int px0 = (int)(ent & 0xfffu) * 4;
         uint32_t todo = ent >> 12;
+        PF_CHECK(px0 + 3 < P || todo == 0u);
         const int row = (int)__umulhi((uint32_t)px0, p.w_magic), col = px0 - row * p.W;
         while (__any_sync(0xffffffffu, todo != 0u)) {
           if (todo != 0u) {
@@ -359,6 +366,7 @@ __device__ __forceinline__ void crop_pass2(const FwdParams& p, const unsigned ch
     // groups with valid pixels that are NOT inliers go to the warp's queue
     const uint32_t pending = okb & ~inb & ~band;
     const uint32_t b = __ballot_sync(0xffffffffu, pending != 0u);
+    PF_CHECK(qn + 32 <= qcap && (i4 >> 2) < 4096);
     if (pending != 0u) q[qn + __popc(b & lt)] = (uint16_t)((uint32_t)(i4 >> 2) | (pending << 12));
     qn += __popc(b);
   }
@@ -544,6 +552,7 @@ __global__ void __launch_bounds__(NT, 3) fit_ransac_crop_kernel(const FwdParams 
       uint32_t qi = (r0 + 1u) >> 1;
       const int base = w * 32;
       while (e != 0u) {
+        PF_CHECK(qi < (uint32_t)(P / 2));
         klist[qi++] = (uint16_t)(base + __ffs(e) - 1);
         e &= e - 1u;
       }
@@ -571,8 +580,10 @@ __global__ void __launch_bounds__(NT, 3) fit_ransac_crop_kernel(const FwdParams 
         for (int j = 0; j < p.n_samp; ++j) {
           const int k = sample_index(k_next, N, p.idx_bits);              // pose_utils.py:73
           if (j + 1 < p.n_samp) k_next = __ldg(gi + j + 1);
+          PF_CHECK(k >= 0 && k < N);
           const int px = select_px_list(klist, bits, k);
           const int row = (int)__umulhi((uint32_t)px, p.w_magic), col = px - row * p.W;
+          PF_CHECK(px >= 0 && px < P && row < p.H && col < p.W);
           const float z = sdep[px];
           const float xs[3] = {snoc[px] - 0.5f, snoc[P + px] - 0.5f, snoc[2 * P + px] - 0.5f};   // pose_estimation.py:323
           const float ys[3] = {rxf[col] * z, -(ryf[row] * z), -z};                                // :34-41

@@ -10,6 +10,17 @@
 #include "posefit.h"
 #include "posefit_math.h"
 
+// Debug build only (make EXTRA=-DPF_BOUNDS OUT=...): every computed index of the three hot kernels -- shared-memory
+// rings, tables, bitmap, select list, queues, per-object global offsets -- is range-checked; a violation traps (the
+// launch fails with an error) instead of corrupting memory.  compute-sanitizer is closed on this pool, so this
+// build, run by tests/test_gpu_guards.py, is the memory-safety evidence for reads and shared memory (the guard-zone
+// test only sees stray global WRITES).
+#ifdef PF_BOUNDS
+#define PF_CHECK(cond) do { if (!(cond)) __trap(); } while (0)
+#else
+#define PF_CHECK(cond) do { } while (0)
+#endif
+
 namespace posefit {
 
 constexpr int kAccPlain = 17;     // n, sx3, sy3, syx9, sxx

@@ -104,3 +104,43 @@ def test_no_write_outside_outputs(pf, h, w, b, n_hyp):
                                    ws_plain - 1, stream)
         assert code != 0
     np.testing.assert_equal(arena.guards_intact(), True)
+
+
+def test_bounds_checked_build_runs_clean():
+    """compute-sanitizer is closed on this pool; the -DPF_BOUNDS build of the library (csrc/Makefile: bounds) checks every
+    computed index of the three hot kernels -- shared-memory rings and tables, bitmap, select list, queues, per-object
+    offsets -- and traps on a violation.  A representative workload (plain fit, both RANSAC kernels with several
+    objects per CTA, backward, ragged shapes, sparse masks) must run through it without an error, and give the same
+    results as the product build."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib = os.path.join(root, '3d_mot_differentiable_pose_estimation_b200', 'libposefit_b200_bounds.so')
+    if not os.path.exists(lib):
+        pytest.skip('bounds build not present (make -C csrc bounds)')
+    code = r"""
+import importlib, sys, torch
+pf = importlib.import_module('3d_mot_differentiable_pose_estimation_b200')
+out = []
+for (b, h, w, kw) in [(1500, 64, 64, {}), (40, 112, 112, {}), (64, 19, 27, dict(align_x0=1)), (300, 32, 32, dict(mask_fill=0.1, border=0)),
+                      (64, 48, 64, dict(outlier_frac=0.4)), (16, 64, 64, dict(outlier_frac=0.0, noc_noise=0.0))]:
+    d = pf.synth.make_objects(b, h, w, seed=7, n_hyp=64, device='cuda', **kw)
+    g = (torch.ones(b, device='cuda'), torch.ones(b, 9, device='cuda'), torch.ones(b, 3, device='cuda'))
+    raw = pf.pose_fit_raw(d['noc'], d['depth'], d['mask'], d['bbox_xy0'])
+    rr = pf.pose_fit_raw(d['noc'], d['depth'], d['mask'], d['bbox_xy0'], sample_idx=d['sample_idx'])
+    gn, _ = pf.pose_fit_backward_raw(d['noc'], d['depth'], d['mask'], rr.inlier_mask, d['bbox_xy0'], None, rr.ctx, rr.status, *g)
+    torch.cuda.synchronize()
+    out.append((float(raw.pose[:, :13].sum()), float(rr.pose[:, :13].sum()), int(rr.inlier_mask.sum()), float(gn.double().abs().sum())))
+print(repr(out))
+"""
+    results = []
+    for which in (lib, ''):
+        env = dict(os.environ)
+        env.pop('POSEFIT_LIB', None)
+        if which:
+            env['POSEFIT_LIB'] = which
+        res = subprocess.run([sys.executable, '-c', code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
+        assert res.returncode == 0, res.stderr[-2000:]
+        results.append(res.stdout.strip().splitlines()[-1])
+    assert results[0] == results[1], results
