@@ -27,7 +27,8 @@ SYMBOLS = ('posefit_version', 'posefit_error_string', 'posefit_workspace_bytes',
            'posefit_points_evaluate', 'posefit_transform_points', 'posefit_epilogue', 'posefit_clip_mask', 'posefit_sor_mask',
            'posefit_sor_workspace_bytes', 'posefit_resample_noc', 'posefit_resample_noc_backward',
            'posefit_gather_crops', 'posefit_edge_features', 'posefit_edge_workspace_bytes',
-           'posefit_debug_reload_env', 'posefit_forward_ex', 'posefit_forward_ransac_ex')
+           'posefit_debug_reload_env', 'posefit_forward_ex', 'posefit_forward_ransac_ex',
+           'posefit_forward_head', 'posefit_backward_head', 'posefit_head_workspace_bytes')
 
 _lock = threading.Lock()
 _lib = None
@@ -77,6 +78,14 @@ def _declare(lib):
     lib.posefit_forward_ransac_ex.restype = i32
     lib.posefit_forward_ransac_ex.argtypes = [vp, vp, vp, vp, vp, i32, vp, i32, i32, i32, i32, i32, f64, i32,
                                               vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]
+    lib.posefit_head_workspace_bytes.restype = sz
+    lib.posefit_head_workspace_bytes.argtypes = [i32]
+    lib.posefit_forward_head.restype = i32
+    lib.posefit_forward_head.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp,
+                                         vp, sz, vp]
+    lib.posefit_backward_head.restype = i32
+    lib.posefit_backward_head.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp,
+                                          vp, vp, sz, vp]
     lib.posefit_backward.restype = i32
     lib.posefit_backward.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]
     lib.posefit_backward_workspace_bytes.restype = sz

@@ -613,6 +613,49 @@ __device__ __forceinline__ BilinearTap bilinear_tap(float y, float x, int height
   return t;
 }
 
+// One output pixel (ph, pw) of the resize: forward, v[c] = mean over the bin's grid_h x grid_w bilinear taps of channel
+// c of `smap`; backward, the adjoint: v[c] holds the pixel's gradient and is scattered into `sgrad` (shared-memory
+// atomics).  K-resample and the head-fed fit kernels (fit_head.cuh) share this function, so a NOC value sampled on the
+// fly is bit-identical to the one a materialised crop would hold.
+template <bool BACKWARD>
+__device__ __forceinline__ void sample_head(const float* smap, float* sgrad, int hw, int Hh, int Wh, int ph, int pw,
+                                            float bin_h, float bin_w, int grid_h, int grid_w, float count, float (&v)[3]) {
+  const float roi_start = -0.5f;                              // ROI = the whole map, aligned: offset 0.5
+  float acc[3] = {0.0f, 0.0f, 0.0f}, g[3] = {0.0f, 0.0f, 0.0f};
+  if (BACKWARD) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) g[c] = v[c] / count;
+  }
+  for (int iy = 0; iy < grid_h; ++iy) {
+    const float yy = __fadd_rn(__fadd_rn(roi_start, __fmul_rn((float)ph, bin_h)),
+                               __fdiv_rn(__fmul_rn((float)iy + 0.5f, bin_h), (float)grid_h));
+    for (int ix = 0; ix < grid_w; ++ix) {
+      const float xx = __fadd_rn(__fadd_rn(roi_start, __fmul_rn((float)pw, bin_w)),
+                                 __fdiv_rn(__fmul_rn((float)ix + 0.5f, bin_w), (float)grid_w));
+      const BilinearTap t = bilinear_tap(yy, xx, Hh, Wh);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        if (!BACKWARD) {
+          const float* m = smap + c * hw;
+          const float val = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(t.w1, m[t.pos1]), __fmul_rn(t.w2, m[t.pos2])),
+                                                __fmul_rn(t.w3, m[t.pos3])), __fmul_rn(t.w4, m[t.pos4]));
+          acc[c] = __fadd_rn(acc[c], val);
+        } else {
+          float* m = sgrad + c * hw;
+          atomicAdd(m + t.pos1, g[c] * t.w1);
+          atomicAdd(m + t.pos2, g[c] * t.w2);
+          atomicAdd(m + t.pos3, g[c] * t.w3);
+          atomicAdd(m + t.pos4, g[c] * t.w4);
+        }
+      }
+    }
+  }
+  if (!BACKWARD) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) v[c] = acc[c] / count;
+  }
+}
+
 template <bool BACKWARD>
 __global__ void __launch_bounds__(256) resample_noc_kernel(const ResampleParams p) {
   extern __shared__ __align__(16) float smap[];               // [3][Hh][Wh] head map (fwd) / gradient (bwd)
@@ -628,8 +671,7 @@ __global__ void __launch_bounds__(256) resample_noc_kernel(const ResampleParams 
   const int oh = p.roi_hw[2 * obj], ow = p.roi_hw[2 * obj + 1];
   const int P = p.H * p.W;
   float* crop = p.crop + (size_t)obj * 3 * P;
-  // ROI = the whole map: x1 = y1 = 0, x2 = Wh, y2 = Hh, spatial_scale 1, aligned -> offset 0.5
-  const float roi_start = -0.5f;
+  // ROI = the whole map: x1 = y1 = 0, x2 = Wh, y2 = Hh, spatial_scale 1, aligned -> offset 0.5 (sample_head)
   const float roi_h = (float)p.Hh, roi_w = (float)p.Wh;       // (Hh - 0.5) - (-0.5)
   const float bin_h = oh > 0 ? roi_h / (float)oh : 0.0f, bin_w = ow > 0 ? roi_w / (float)ow : 0.0f;
   const int grid_h = oh > 0 ? (int)ceilf(roi_h / (float)oh) : 1, grid_w = ow > 0 ? (int)ceilf(roi_w / (float)ow) : 1;
@@ -637,40 +679,15 @@ __global__ void __launch_bounds__(256) resample_noc_kernel(const ResampleParams 
   for (int i = tid; i < P; i += 256) {
     const int ph = i / p.W, pw = i - ph * p.W;
     const bool inside = ph < oh && pw < ow;
-    float acc[3] = {0.0f, 0.0f, 0.0f};
-    float g[3] = {0.0f, 0.0f, 0.0f};
+    float v[3] = {0.0f, 0.0f, 0.0f};
     if (BACKWARD && inside) {
 #pragma unroll
-      for (int c = 0; c < 3; ++c) g[c] = crop[c * P + i] / count;
+      for (int c = 0; c < 3; ++c) v[c] = crop[c * P + i];
     }
-    if (inside) {
-      for (int iy = 0; iy < grid_h; ++iy) {
-        const float yy = __fadd_rn(__fadd_rn(roi_start, __fmul_rn((float)ph, bin_h)),
-                                   __fdiv_rn(__fmul_rn((float)iy + 0.5f, bin_h), (float)grid_h));
-        for (int ix = 0; ix < grid_w; ++ix) {
-          const float xx = __fadd_rn(__fadd_rn(roi_start, __fmul_rn((float)pw, bin_w)),
-                                     __fdiv_rn(__fmul_rn((float)ix + 0.5f, bin_w), (float)grid_w));
-          const BilinearTap t = bilinear_tap(yy, xx, p.Hh, p.Wh);
-#pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            float* m = smap + c * hw;
-            if (!BACKWARD) {
-              const float v = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(t.w1, m[t.pos1]), __fmul_rn(t.w2, m[t.pos2])),
-                                                  __fmul_rn(t.w3, m[t.pos3])), __fmul_rn(t.w4, m[t.pos4]));
-              acc[c] = __fadd_rn(acc[c], v);
-            } else {
-              atomicAdd(m + t.pos1, g[c] * t.w1);
-              atomicAdd(m + t.pos2, g[c] * t.w2);
-              atomicAdd(m + t.pos3, g[c] * t.w3);
-              atomicAdd(m + t.pos4, g[c] * t.w4);
-            }
-          }
-        }
-      }
-    }
+    if (inside) sample_head<BACKWARD>(smap, smap, hw, p.Hh, p.Wh, ph, pw, bin_h, bin_w, grid_h, grid_w, count, v);
     if (!BACKWARD) {
 #pragma unroll
-      for (int c = 0; c < 3; ++c) crop[c * P + i] = inside ? acc[c] / count : 0.0f;
+      for (int c = 0; c < 3; ++c) crop[c * P + i] = inside ? v[c] : 0.0f;
     }
   }
   if (BACKWARD) {

@@ -120,6 +120,29 @@ int posefit_forward_ransac_ex(const float* noc, const float* depth, const uint8_
                               float* scale_f32, float* rot_f32, float* trans_f32,
                               void* workspace, size_t workspace_bytes, void* stream);
 
+/* The plain fit and its gradient fed by the NOC HEAD OUTPUT instead of a materialised NOC crop.
+ * Replaces, per object: the per-instance roi_align resize of the 3 x 28 x 28 head output to the instance's box
+ * (Detection/tracker/postprocess.py:141-147, head: Detection/roi_heads/nocs_head.py:232-235) AND the fit it feeds
+ * (posefit_forward): head[b][3][head_h][head_w] (float32) is sampled on the fly with torchvision's roi_align taps
+ * (aligned, whole map, output size roi_hw[b] = (h_b, w_b), zero padding to height x width) -- bit-identical values to
+ * posefit_resample_noc -- so no h x w x 3 patch is ever written or read.  depth / mask / bbox_xy0 / kinv and all
+ * outputs as for posefit_forward_ex.  posefit_backward_head is the matching adjoint: gradient w.r.t. the head output
+ * (grad_head [B][3][head_h][head_w], fully written) and optionally the depth crop. */
+size_t posefit_head_workspace_bytes(int n_objects);
+int posefit_forward_head(const float* head, const int32_t* roi_hw, const float* depth, const uint8_t* mask,
+                         const int32_t* bbox_xy0, const double* kinv, int kinv_per_object,
+                         int n_objects, int head_h, int head_w, int height, int width,
+                         double* pose, double* ctx, int32_t* status, int32_t* n_valid,
+                         float* scale_f32, float* rot_f32, float* trans_f32,
+                         void* workspace, size_t workspace_bytes, void* stream);
+int posefit_backward_head(const float* head, const int32_t* roi_hw, const float* depth, const uint8_t* mask,
+                          const uint8_t* inlier_mask, const int32_t* bbox_xy0, const double* kinv, int kinv_per_object,
+                          int n_objects, int head_h, int head_w, int height, int width,
+                          const double* ctx, const int32_t* status,
+                          const float* grad_scale, const float* grad_R, const float* grad_t,
+                          float* grad_head, float* grad_depth,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
 /* Points mode: the same two fits on explicit correspondences, for callers that hold point sets
  * rather than crops -- the argument form of estimateSimilarityUmeyama / estimateSimilarityTransform
  * themselves (PoseEst/pose_utils.py:16, :86; run_pose calls them on filtered clouds,

@@ -249,3 +249,43 @@ def test_run_pose_batched_bucketed_equals_single_canvas(pf):
         grads.append(hd.grad.clone())
     assert torch.isfinite(grads[0]).all() and float(grads[0].abs().max()) > 0
     assert float((grads[0] - grads[1]).abs().max()) <= 1e-5 * float(grads[0].abs().max())
+
+
+def test_head_fed_fit_equals_resample_then_fit(pf):
+    """posefit_forward_head / posefit_backward_head (the roi_align resize fused into the fit's loaders)
+    against the composition it replaces, resample_noc -> pose_fit: poses to rounding (the sampled NOC values are
+    bit-identical, only the summation order differs), head and depth gradients to 1e-4 relative (float atomics).  Boxes
+    smaller than the head map (several taps per pixel), larger, ragged canvas, empty instances, per-object intrinsics."""
+    rng = np.random.default_rng(11)
+    for (b, h, w, seed, per_obj) in [(48, 64, 64, 1, False), (24, 40, 52, 2, False), (12, 19, 27, 3, True), (6, 112, 112, 4, False)]:
+        d = pf.synth.make_objects(b, h, w, seed=700 + seed, device='cuda', align_x0=1 if w % 4 else 4)
+        head0 = torch.nn.functional.adaptive_avg_pool2d(d['noc'], 28).contiguous()
+        roi = torch.from_numpy(np.stack([rng.integers(max(h // 4, 2), h + 1, size=b), rng.integers(max(w // 4, 2), w + 1, size=b)],
+                                        axis=1).astype(np.int32)).cuda()
+        roi[0] = torch.tensor([h, w], dtype=torch.int32)
+        mask = d['mask'].clone()
+        mask[1] = 0                                                       # an instance without correspondences
+        kinv = None
+        if per_obj:
+            kinv = pf.default_kinv('cuda').repeat(b, 1, 1).contiguous()
+            kinv[:, 0, 1] = 1e-4                                          # skewed: the general back-projection
+        g = (torch.randn(b, device='cuda'), torch.randn(b, 3, 3, device='cuda'), torch.randn(b, 3, device='cuda'))
+
+        def run(fused):
+            head = head0.clone().requires_grad_(True)
+            depth = d['depth'].clone().requires_grad_(True)
+            if fused:
+                s_, r_, t_, status, n_valid = pf.pose_fit_head(head, roi, depth, mask, d['bbox_xy0'], kinv)
+            else:
+                noc = pf.resample_noc(head, roi, h, w)
+                s_, r_, t_, _, status, n_valid = pf.pose_fit(noc, depth, mask, d['bbox_xy0'], kinv)
+            torch.autograd.backward((s_, r_, t_), g)
+            return s_.detach(), r_.detach(), t_.detach(), status, n_valid, head.grad, depth.grad
+        a, c = run(True), run(False)
+        torch.cuda.synchronize()
+        assert torch.equal(a[3], c[3]) and torch.equal(a[4], c[4])
+        assert int(a[3][1]) == 1
+        for x, y in zip(a[:3], c[:3]):
+            assert float((x - y).abs().max()) <= 2e-6 * max(float(y.abs().max()), 1.0)
+        for x, y in zip(a[5:], c[5:]):
+            assert float((x - y).abs().max()) <= 1e-4 * float(y.abs().max()), (h, w, float((x - y).abs().max()), float(y.abs().max()))
