@@ -613,69 +613,141 @@ __device__ __forceinline__ BilinearTap bilinear_tap(float y, float x, int height
   return t;
 }
 
+// Per-axis tap tables of one object's resize.  The sample coordinate of output row ph, tap iy is
+//   yy = (roi_start + ph * bin_h) + ((iy + 0.5) * bin_h) / grid_h          (torchvision roi_align, aligned = True)
+// and depends on nothing else, so its bilinear decomposition (pre_calc_for_bilinear_interpolate: clamp, low / high
+// cell, weights l and h = 1 - l) is computed ONCE per (row, tap) and per (column, tap) instead of once per pixel,
+// channel and tap -- same float operations in the same order, only hoisted.  Entry = { low, high, l, h } (16 bytes);
+// rows store low / high already multiplied by the map width.  n entries = size * grid.
+struct TapEntry {
+  int lo, hi;
+  float l, h;
+};
+
+__device__ __forceinline__ TapEntry tap_entry(int p, int it, float bin, int grid, int extent, int stride) {
+  const float roi_start = -0.5f;                              // ROI = the whole map, aligned: offset 0.5
+  float y = __fadd_rn(__fadd_rn(roi_start, __fmul_rn((float)p, bin)), __fdiv_rn(__fmul_rn((float)it + 0.5f, bin), (float)grid));
+  TapEntry e;
+  if (y < -1.0f || y > (float)extent) {                      // outside the map: the tap contributes nothing
+    e.lo = e.hi = 0;
+    e.l = e.h = 0.0f;
+    return e;
+  }
+  if (y <= 0.0f) y = 0.0f;
+  int lo = (int)y, hi;
+  if (lo >= extent - 1) { hi = lo = extent - 1; y = (float)lo; } else { hi = lo + 1; }
+  e.l = __fsub_rn(y, (float)lo);
+  e.h = __fsub_rn(1.0f, e.l);
+  e.lo = lo * stride;
+  e.hi = hi * stride;
+  return e;
+}
+
+// rows[oh * grid_h], cols[ow * grid_w]; all threads of the CTA take part (caller synchronises afterwards)
+__device__ __forceinline__ void build_tap_tables(TapEntry* rows, TapEntry* cols, int oh, int ow, float bin_h, float bin_w,
+                                                 int grid_h, int grid_w, int Hh, int Wh, int tid, int nt) {
+  for (int e = tid; e < oh * grid_h; e += nt) rows[e] = tap_entry(e / grid_h, e - (e / grid_h) * grid_h, bin_h, grid_h, Hh, Wh);
+  for (int e = tid; e < ow * grid_w; e += nt) cols[e] = tap_entry(e / grid_w, e - (e / grid_w) * grid_w, bin_w, grid_w, Wh, 1);
+}
+
 // One output pixel (ph, pw) of the resize: forward, v[c] = mean over the bin's grid_h x grid_w bilinear taps of channel
 // c of `smap`; backward, the adjoint: v[c] holds the pixel's gradient and is scattered into `sgrad` (shared-memory
 // atomics).  K-resample and the head-fed fit kernels (fit_head.cuh) share this function, so a NOC value sampled on the
-// fly is bit-identical to the one a materialised crop would hold.
+// fly is bit-identical to the one a materialised crop would hold.  (A tap outside the map has l = h = 0: torchvision
+// zeroes all four weights when EITHER coordinate is outside, which the products below reproduce.)
 template <bool BACKWARD>
-__device__ __forceinline__ void sample_head(const float* smap, float* sgrad, int hw, int Hh, int Wh, int ph, int pw,
-                                            float bin_h, float bin_w, int grid_h, int grid_w, float count, float (&v)[3]) {
-  const float roi_start = -0.5f;                              // ROI = the whole map, aligned: offset 0.5
+__device__ __forceinline__ void sample_head(const float* smap, float* sgrad, int hw, const TapEntry* rows, const TapEntry* cols,
+                                            int ph, int pw, int grid_h, int grid_w, float count, float (&v)[3]) {
   float acc[3] = {0.0f, 0.0f, 0.0f}, g[3] = {0.0f, 0.0f, 0.0f};
   if (BACKWARD) {
 #pragma unroll
-    for (int c = 0; c < 3; ++c) g[c] = v[c] / count;
+    for (int c = 0; c < 3; ++c) g[c] = count != 1.0f ? v[c] / count : v[c];
   }
+#pragma unroll 1
   for (int iy = 0; iy < grid_h; ++iy) {
-    const float yy = __fadd_rn(__fadd_rn(roi_start, __fmul_rn((float)ph, bin_h)),
-                               __fdiv_rn(__fmul_rn((float)iy + 0.5f, bin_h), (float)grid_h));
+    const TapEntry ry = rows[ph * grid_h + iy];
+#pragma unroll 1
     for (int ix = 0; ix < grid_w; ++ix) {
-      const float xx = __fadd_rn(__fadd_rn(roi_start, __fmul_rn((float)pw, bin_w)),
-                                 __fdiv_rn(__fmul_rn((float)ix + 0.5f, bin_w), (float)grid_w));
-      const BilinearTap t = bilinear_tap(yy, xx, Hh, Wh);
+      const TapEntry cx = cols[pw * grid_w + ix];
+      const float w1 = __fmul_rn(ry.h, cx.h), w2 = __fmul_rn(ry.h, cx.l), w3 = __fmul_rn(ry.l, cx.h), w4 = __fmul_rn(ry.l, cx.l);
+      const int pos1 = ry.lo + cx.lo, pos2 = ry.lo + cx.hi, pos3 = ry.hi + cx.lo, pos4 = ry.hi + cx.hi;
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         if (!BACKWARD) {
           const float* m = smap + c * hw;
-          const float val = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(t.w1, m[t.pos1]), __fmul_rn(t.w2, m[t.pos2])),
-                                                __fmul_rn(t.w3, m[t.pos3])), __fmul_rn(t.w4, m[t.pos4]));
+          const float val = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w1, m[pos1]), __fmul_rn(w2, m[pos2])),
+                                                __fmul_rn(w3, m[pos3])), __fmul_rn(w4, m[pos4]));
           acc[c] = __fadd_rn(acc[c], val);
         } else {
           float* m = sgrad + c * hw;
-          atomicAdd(m + t.pos1, g[c] * t.w1);
-          atomicAdd(m + t.pos2, g[c] * t.w2);
-          atomicAdd(m + t.pos3, g[c] * t.w3);
-          atomicAdd(m + t.pos4, g[c] * t.w4);
+          atomicAdd(m + pos1, g[c] * w1);
+          atomicAdd(m + pos2, g[c] * w2);
+          atomicAdd(m + pos3, g[c] * w3);
+          atomicAdd(m + pos4, g[c] * w4);
         }
       }
     }
   }
   if (!BACKWARD) {
 #pragma unroll
-    for (int c = 0; c < 3; ++c) v[c] = acc[c] / count;
+    for (int c = 0; c < 3; ++c) v[c] = count != 1.0f ? acc[c] / count : acc[c];
   }
+}
+
+// The common case -- the box is at least as large as the map, ONE tap per pixel (grid 1 x 1, count 1) -- without the tap
+// loops: same operations in the same order as sample_head for that case.  `ry` is the pixel's row entry (shared by the
+// pixels of a row, loaded once by the caller).
+template <bool BACKWARD>
+__device__ __forceinline__ void sample_head_1tap(const float* smap, float* sgrad, int hw, const TapEntry& ry, const TapEntry& cx,
+                                                 float (&v)[3]) {
+  const float w1 = __fmul_rn(ry.h, cx.h), w2 = __fmul_rn(ry.h, cx.l), w3 = __fmul_rn(ry.l, cx.h), w4 = __fmul_rn(ry.l, cx.l);
+  const int pos1 = ry.lo + cx.lo, pos2 = ry.lo + cx.hi, pos3 = ry.hi + cx.lo, pos4 = ry.hi + cx.hi;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    if (!BACKWARD) {
+      const float* m = smap + c * hw;
+      // (0 + val: sample_head starts its accumulator at zero; adding it is exact)
+      v[c] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w1, m[pos1]), __fmul_rn(w2, m[pos2])), __fmul_rn(w3, m[pos3])),
+                       __fmul_rn(w4, m[pos4]));
+    } else {
+      float* m = sgrad + c * hw;
+      atomicAdd(m + pos1, v[c] * w1);
+      atomicAdd(m + pos2, v[c] * w2);
+      atomicAdd(m + pos3, v[c] * w3);
+      atomicAdd(m + pos4, v[c] * w4);
+    }
+  }
+}
+
+// bytes of shared memory the two tap tables need for a height x width canvas and an Hh x Wh map
+static inline size_t tap_table_bytes(int hh, int wh, int height, int width) {
+  const int nr = height > 2 * hh ? height : 2 * hh, nc = width > 2 * wh ? width : 2 * wh;
+  return (size_t)(nr + nc) * sizeof(TapEntry);
 }
 
 template <bool BACKWARD>
 __global__ void __launch_bounds__(256) resample_noc_kernel(const ResampleParams p) {
-  extern __shared__ __align__(16) float smap[];               // [3][Hh][Wh] head map (fwd) / gradient (bwd)
+  extern __shared__ __align__(16) float smap[];               // [3][Hh][Wh] head map (fwd) / gradient (bwd) | tap tables
   const int obj = blockIdx.x, tid = threadIdx.x;
   const int hw = p.Hh * p.Wh;
+  TapEntry* rows = reinterpret_cast<TapEntry*>(smap + ((3 * hw + 3) & ~3));
+  TapEntry* cols = rows + (p.H > 2 * p.Hh ? p.H : 2 * p.Hh);
   const float* head = p.head + (size_t)obj * 3 * hw;
   if (!BACKWARD) {
     for (int i = tid; i < 3 * hw; i += 256) smap[i] = head[i];
   } else {
     for (int i = tid; i < 3 * hw; i += 256) smap[i] = 0.0f;
   }
-  __syncthreads();
   const int oh = p.roi_hw[2 * obj], ow = p.roi_hw[2 * obj + 1];
   const int P = p.H * p.W;
   float* crop = p.crop + (size_t)obj * 3 * P;
-  // ROI = the whole map: x1 = y1 = 0, x2 = Wh, y2 = Hh, spatial_scale 1, aligned -> offset 0.5 (sample_head)
+  // ROI = the whole map: x1 = y1 = 0, x2 = Wh, y2 = Hh, spatial_scale 1, aligned -> offset 0.5 (tap_entry)
   const float roi_h = (float)p.Hh, roi_w = (float)p.Wh;       // (Hh - 0.5) - (-0.5)
   const float bin_h = oh > 0 ? roi_h / (float)oh : 0.0f, bin_w = ow > 0 ? roi_w / (float)ow : 0.0f;
   const int grid_h = oh > 0 ? (int)ceilf(roi_h / (float)oh) : 1, grid_w = ow > 0 ? (int)ceilf(roi_w / (float)ow) : 1;
   const float count = (float)max(grid_h * grid_w, 1);
+  build_tap_tables(rows, cols, min(oh, p.H), min(ow, p.W), bin_h, bin_w, grid_h, grid_w, p.Hh, p.Wh, tid, 256);
+  __syncthreads();
   for (int i = tid; i < P; i += 256) {
     const int ph = i / p.W, pw = i - ph * p.W;
     const bool inside = ph < oh && pw < ow;
@@ -684,7 +756,7 @@ __global__ void __launch_bounds__(256) resample_noc_kernel(const ResampleParams 
 #pragma unroll
       for (int c = 0; c < 3; ++c) v[c] = crop[c * P + i];
     }
-    if (inside) sample_head<BACKWARD>(smap, smap, hw, p.Hh, p.Wh, ph, pw, bin_h, bin_w, grid_h, grid_w, count, v);
+    if (inside) sample_head<BACKWARD>(smap, smap, hw, rows, cols, ph, pw, grid_h, grid_w, count, v);
     if (!BACKWARD) {
 #pragma unroll
       for (int c = 0; c < 3; ++c) crop[c * P + i] = inside ? v[c] : 0.0f;

@@ -683,6 +683,43 @@ def run_ours(args):
             'note': 'public torch.autograd.Function (pose_fit, kinv=None) + autograd backward, eager launches; scale / R / t '
                     'are written as float32 by the solve kernel (no eager torch arithmetic on the batch)'}
 
+        # ---- the same shard fed by the NOC HEAD OUTPUTS: the roi_align resize fused into the loaders of the
+        # fit and of its backward pass (PoseFitHead) against the composition it replaces (resample_noc -> pose_fit)
+        head_dev = torch.nn.functional.adaptive_avg_pool2d(d['noc'], 28).contiguous()
+        roi_dev = torch.tensor([[size, size]], dtype=torch.int32, device=dev).repeat(n_obj, 1)
+
+        def head_step(fused):
+            head = head_dev.requires_grad_(True)
+            head.grad = None
+            if fused:
+                scale, rot, trans, _, _ = pf.pose_fit_head(head, roi_dev, d['depth'], d['mask'], d['bbox_xy0'])
+            else:
+                noc = pf.resample_noc(head, roi_dev, size, size)
+                scale, rot, trans, _, _, _ = pf.pose_fit(noc, d['depth'], d['mask'], d['bbox_xy0'])
+            torch.autograd.backward((scale, rot, trans), (g_s, g_R33, g_t))
+        ms_head = {}
+        for fused in (True, False):
+            for _ in range(2):
+                head_step(fused)
+            torch.cuda.synchronize()
+            a0, a1 = ev(), ev()
+            a0.record()
+            for _ in range(5):
+                head_step(fused)
+            a1.record()
+            torch.cuda.synchronize()
+            ms_head[fused] = a0.elapsed_time(a1) / 5
+        hb = 3 * 28 * 28 * 4
+        b_head = n_obj * ((5 * P + hb + 64) + (5 * P + hb + 52 + hb))
+        configs['C5 shard from head outputs (fused loaders)'] = {
+            'ms': ms_head[True], 'objects_per_s': n_obj / ms_head[True] * 1e3, 'gbs': b_head / ms_head[True] / 1e6,
+            'frac': b_head / ms_head[True] / 1e6 / hbm_peak, 'composed_ms': ms_head[False],
+            'note': 'pose_fit_head + backward: 3x28x28 head outputs sampled inside the loaders (%.1f KB of algorithmic traffic '
+                    'per object instead of %.1f KB for resample_noc -> pose_fit -> backward -> resample backward); these '
+                    'kernels are bound by instruction issue (bilinear taps, shared-memory atomics), not by HBM'
+                    % (b_head / n_obj / 1e3, (46 * P + 24 * P + 2 * hb) / 1e3)}
+        del head_dev, roi_dev
+
         # ---- config 5 as written: 1,000,000 objects on ONE GPU (69.6 GB of inputs + 49 GB of NOC gradient)
         if world == 1 and not args.no_full and n_obj < TOTAL_OBJECTS:
             free_b, _ = torch.cuda.mem_get_info()
