@@ -795,7 +795,7 @@ def run_ours(args):
             'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': int(launches),
             'clocks': clk.summary(), 'configs': configs,
         }
-        print(json.dumps(line))
+        _emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -832,11 +832,23 @@ def run_reference(args):
                              'sample': what},
             'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
-    print(json.dumps(line))
+    _emit(line)
 
+
+def _emit(line):
+    """The ONE line of stdout.  Everything else a run writes to file descriptor 1 -- NCCL's own `NCCL version ...`
+    banner at communicator creation, a library's stray printf -- was pointed at stderr by main()."""
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT, (json.dumps(line) + '\n').encode())
+
+
+_REAL_STDOUT = 1
 
 if __name__ == '__main__':
     a = parse()
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if a.impl == 'reference':
         run_reference(a)
     else:
