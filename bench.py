@@ -763,10 +763,21 @@ def run_ours(args):
                 a1.record()
                 torch.cuda.synchronize()
                 ms_big = a0.elapsed_time(a1) / k_big
+                f0, f1, f2 = ev(), ev(), ev()                     # one more step, forward and backward apart
+                f0.record()
+                raw_b = pf.pose_fit_raw(big['noc'], big['depth'], big['mask'], big['bbox_xy0'], kinv)
+                f1.record()
+                pf.pose_fit_backward_raw(big['noc'], big['depth'], big['mask'], None, big['bbox_xy0'], kinv, raw_b.ctx,
+                                         raw_b.status, *bg, out=g_noc)
+                f2.record()
+                torch.cuda.synchronize()
+                del raw_b
                 b_big = TOTAL_OBJECTS * (17 * P + 64 + 29 * P + 52)
                 configs['C5 1M @ N=1'] = {'ms': ms_big, 'objects_per_s': TOTAL_OBJECTS / ms_big * 1e3,
                                           'gbs': b_big / ms_big / 1e6, 'frac': b_big / ms_big / 1e6 / hbm_peak,
-                                          'steps': k_big, 'note': 'BASELINE config 5 on one GPU: 1,000,000 objects fwd + bwd per step'}
+                                          'steps': k_big, 'fwd_ms': f0.elapsed_time(f1), 'bwd_ms': f1.elapsed_time(f2),
+                                          'free_gb_before': free_b / 1e9,
+                                          'note': 'BASELINE config 5 on one GPU: 1,000,000 objects fwd + bwd per step'}
                 del big, bg, g_noc
                 torch.cuda.empty_cache()
             else:
