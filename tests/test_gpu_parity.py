@@ -354,7 +354,8 @@ def test_launch_variants_agree(pf, knob):
                 {'POSEFIT_RANSAC_THREADS': '256'}, {'POSEFIT_RANSAC_SCREEN': '0', 'POSEFIT_RANSAC_THREADS': '256'},
                 {'POSEFIT_RANSAC_SCREEN': '0', 'POSEFIT_RANSAC_THREADS': '256', 'POSEFIT_RANSAC_MINB': '3'},
                 {'POSEFIT_RANSAC_SCREEN': '0', 'POSEFIT_NO_IDX_PRELOAD': '1'},
-                {'POSEFIT_RANSAC_SCREEN': '0', 'POSEFIT_NO_EARLY_ISSUE': '1'}]
+                {'POSEFIT_RANSAC_SCREEN': '0', 'POSEFIT_NO_EARLY_ISSUE': '1'},
+                {'POSEFIT_PDL_MASK': '15'}, {'POSEFIT_PDL_MASK': '5'}, {'POSEFIT_BWD_MINB': '3'}, {'POSEFIT_BWD_MINB': '4'}]
     for env in variants:
         for k, v in env.items():
             knob.set(k, v)

@@ -15,7 +15,7 @@ for name, us in head:
     per.setdefault(name, []).append(us)
 step = sum(sum(v) / len(v) for v in per.values())
 with open(out, 'w') as f:
-    f.write('# ncu launch list of `python bench.py --steps 5 --warmup 3 --no-cpu` (r01, final kernels)\n\n')
+    f.write('# ncu launch list of `python bench.py --steps 5 --warmup 3 --no-cpu` (r02, final kernels)\n\n')
     f.write('Command: `ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"fit_|pose_" -c 400 --csv python bench.py --steps 5 --warmup 3 --no-cpu`\n\n')
     f.write('Per-launch times under ncu are cold-cache and serialised: compare SHARES of the step, not absolutes.\n\n')
     f.write('Headline step (config-5 shard, mean of the first 8 steps):\n\n| kernel | us per step | share |\n|---|---|---|\n')
