@@ -26,7 +26,7 @@ SYMBOLS = ('posefit_version', 'posefit_error_string', 'posefit_workspace_bytes',
            'posefit_points_forward', 'posefit_points_forward_ransac', 'posefit_compact',
            'posefit_points_evaluate', 'posefit_transform_points', 'posefit_epilogue', 'posefit_clip_mask', 'posefit_sor_mask',
            'posefit_sor_workspace_bytes', 'posefit_resample_noc', 'posefit_resample_noc_backward',
-           'posefit_gather_crops', 'posefit_edge_features', 'posefit_edge_workspace_bytes',
+           'posefit_gather_crops', 'posefit_unpack_mask', 'posefit_edge_features', 'posefit_edge_workspace_bytes',
            'posefit_debug_reload_env', 'posefit_forward_ex', 'posefit_forward_ransac_ex',
            'posefit_forward_head', 'posefit_backward_head', 'posefit_head_workspace_bytes')
 
@@ -113,6 +113,8 @@ def _declare(lib):
     lib.posefit_resample_noc_backward.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp, vp]
     lib.posefit_gather_crops.restype = i32
     lib.posefit_gather_crops.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp]
+    lib.posefit_unpack_mask.restype = i32
+    lib.posefit_unpack_mask.argtypes = [vp, c.c_longlong, vp, vp]
     lib.posefit_edge_workspace_bytes.restype = sz
     lib.posefit_edge_workspace_bytes.argtypes = [i32, i32, i32, i32]
     lib.posefit_edge_features.restype = i32

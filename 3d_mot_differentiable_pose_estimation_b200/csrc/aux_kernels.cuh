@@ -719,6 +719,28 @@ __device__ __forceinline__ void sample_head_1tap(const float* smap, float* sgrad
   }
 }
 
+
+// ---- instance masks on the wire: one BIT per pixel ------------------------------------------------------------------
+// The detector's instance masks are boolean (Detection/tracker/postprocess.py:134-139 thresholds them); shipping them
+// to the device as bits instead of bytes takes 3.6 KB off the 29.9 KB an object costs on PCIe.  bits: little-endian
+// within a byte (numpy.packbits(..., bitorder='little')): pixel i = bit (i & 7) of byte (i >> 3); mask: 0 / 1 bytes.
+__global__ void __launch_bounds__(256) unpack_mask_kernel(const uint8_t* __restrict__ bits, uint8_t* __restrict__ mask,
+                                                          long long n_pixels, int wide) {
+  const long long n_bytes = (n_pixels + 7) >> 3;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_bytes; i += stride) {
+    const unsigned long long b = (unsigned long long)__ldg(bits + i);
+    // byte k of x keeps bit k of b; + 0x7f carries any non-zero byte into its bit 7
+    unsigned long long x = (b * 0x0101010101010101ULL) & 0x8040201008040201ULL;
+    x = ((x + 0x7f7f7f7f7f7f7f7fULL) >> 7) & 0x0101010101010101ULL;
+    if (wide && 8 * i + 8 <= n_pixels) {
+      __stcs(reinterpret_cast<unsigned long long*>(mask + 8 * i), x);
+    } else {
+      for (int k = 0; k < 8 && 8 * i + k < n_pixels; ++k) mask[8 * i + k] = (uint8_t)((x >> (8 * k)) & 1ULL);
+    }
+  }
+}
+
 // bytes of shared memory the two tap tables need for a height x width canvas and an Hh x Wh map
 static inline size_t tap_table_bytes(int hh, int wh, int height, int width) {
   const int nr = height > 2 * hh ? height : 2 * hh, nc = width > 2 * wh ? width : 2 * wh;

@@ -49,6 +49,33 @@ def gather_crops(depth_frames, inst_masks, boxes_xyxy, frame_of: Optional[torch.
     return Crops(depth, mask, xy0, roi_hw)
 
 
+def pack_mask(mask) -> torch.Tensor:
+    """Host side of the one-bit-per-pixel wire format: mask (bool / 0-1 array or CPU tensor of any shape) ->
+    uint8 CPU tensor of ceil(numel / 8) bytes, pixel i = bit (i & 7) of byte (i >> 3) over the flattened array."""
+    import numpy as np
+    arr = mask.detach().cpu().numpy() if isinstance(mask, torch.Tensor) else np.asarray(mask)
+    return torch.from_numpy(np.packbits(arr.reshape(-1) != 0, bitorder='little'))
+
+
+def unpack_mask(bits: torch.Tensor, shape) -> torch.Tensor:
+    """bits: uint8 CUDA tensor written by `pack_mask` (after its copy to the device) -> uint8 mask of `shape` (0 / 1),
+    the layout every fit entry takes."""
+    if not bits.is_cuda:
+        raise _lib.PoseFitError('unpack_mask needs a CUDA tensor: the solver has no CPU path')
+    shape = tuple(int(v) for v in shape)
+    n = 1
+    for v in shape:
+        n *= v
+    bits = bits.contiguous()
+    if bits.dtype != torch.uint8 or bits.numel() * 8 < n:
+        raise ValueError('bits must be uint8 with at least ceil(numel / 8) bytes')
+    mask = torch.empty(shape, dtype=torch.uint8, device=bits.device)
+    with torch.cuda.device(bits.device):
+        code = _lib.lib().posefit_unpack_mask(_ptr(bits), n, _ptr(mask), _stream(bits.device))
+    _lib.check(code, 'posefit_unpack_mask')
+    return mask
+
+
 class ResampleNoc(torch.autograd.Function):
     """noc[B,3,H,W] = per-instance ROI-align resize of noc_head[B,3,Hh,Wh] to roi_hw[b] = (h_b, w_b),
     zero padded (postprocess.py:141-147).  Gradient flows to noc_head."""

@@ -515,7 +515,11 @@ def run_ours(args):
     head_dev = torch.nn.functional.adaptive_avg_pool2d(d['noc'][:ne], 28).contiguous()      # synthetic head outputs
     roi_dev = torch.tensor([[size, size]], dtype=torch.int32, device=dev).repeat(ne, 1)
     host = {'head': head_dev.cpu().pin_memory(), 'roi_hw': roi_dev.cpu().pin_memory()}
-    host.update({k: d[k][:ne].cpu().pin_memory() for k in ('depth', 'mask', 'bbox_xy0')})
+    host.update({k: d[k][:ne].cpu().pin_memory() for k in ('depth', 'bbox_xy0')})
+    # instance masks cross PCIe as bits (the masks are boolean, postprocess.py:134-139): packed on the host when the
+    # sample is staged, expanded on the device by posefit_unpack_mask inside the timed step
+    host['mask_bits'] = pf.pack_mask(d['mask'][:ne].cpu()).pin_memory()
+    mask_shape = tuple(d['mask'][:ne].shape)
     del head_dev, roi_dev
     hg = {'s': g_s[:ne].cpu().pin_memory(), 'R': g_R[:ne].reshape(ne, 3, 3).cpu().pin_memory(),
           't': g_t[:ne].cpu().pin_memory()}
@@ -535,7 +539,7 @@ def run_ours(args):
     def e2e_upload(sl):
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(sl['free'])                   # the step that last used this set is done
-            for k in ('head', 'roi_hw', 'depth', 'mask', 'bbox_xy0'):
+            for k in ('head', 'roi_hw', 'depth', 'mask_bits', 'bbox_xy0'):
                 sl[k] = host[k].to(dev, non_blocking=True)
             sl['g'] = tuple(hg[k].to(dev, non_blocking=True) for k in ('s', 'R', 't'))
             sl['ready'].record()
@@ -549,11 +553,12 @@ def run_ours(args):
         cur.wait_event(sl['ready'])
         e2e_upload(nxt)                                          # next step's inputs, behind this step's compute
         head = sl['head'].requires_grad_(True)
-        for t in (sl['head'], sl['roi_hw'], sl['depth'], sl['mask'], sl['bbox_xy0']) + sl['g']:
+        for t in (sl['head'], sl['roi_hw'], sl['depth'], sl['mask_bits'], sl['bbox_xy0']) + sl['g']:
             t.record_stream(cur)
         gs, gR, gt = sl['g']
         noc = pf.resample_noc(head, sl['roi_hw'], size, size)
-        scale, rot, trans, _, _, _ = pf.pose_fit(noc, sl['depth'], sl['mask'], sl['bbox_xy0'])
+        mask = pf.unpack_mask(sl['mask_bits'], mask_shape)
+        scale, rot, trans, _, _, _ = pf.pose_fit(noc, sl['depth'], mask, sl['bbox_xy0'])
         torch.autograd.backward((scale, rot, trans), (gs, gR, gt))
         out_host[:, 0].copy_(scale.detach(), non_blocking=True)
         out_host[:, 1:10].copy_(rot.detach().reshape(ne, 9), non_blocking=True)
@@ -582,8 +587,9 @@ def run_ours(args):
         e2e_ms = float(tms)
     e2e = {'value': world * ne / (e2e_ms * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
            'objects_per_step_per_gpu': ne, 'ms_per_step': e2e_ms, 'h2d_gbs': h2d / e2e_ms / 1e6,
-           'inputs': 'per object: 3x28x28 NOC head output + depth / mask windows + box corner + upstream gradients '
-                     '(%.1f KB); resample_noc -> pose_fit -> backward to the head output on the device' % (h2d / ne / 1e3)}
+           'inputs': 'per object: 3x28x28 NOC head output + depth window + bit-packed mask window + box corner + upstream '
+                     'gradients (%.1f KB); unpack_mask -> resample_noc -> pose_fit -> backward to the head output on the '
+                     'device' % (h2d / ne / 1e3)}
     del host, hg
 
     # ---- side measurements: configs 2, 3, 4 (single GPU, rank 0) --------------------------------

@@ -266,6 +266,12 @@ int posefit_gather_crops(const float* depth_frames, const uint8_t* mask_frames, 
                          const int32_t* bbox_xyxy, int n_objects, int frame_h, int frame_w, int height, int width,
                          float* depth, uint8_t* mask, int32_t* bbox_xy0, int32_t* roi_hw, void* stream);
 
+/* Instance masks as they cross PCIe: one bit per pixel.  The masks the pose path receives are boolean
+ * (Detection/tracker/postprocess.py:134-139; PoseEst/pose_estimation.py:23-25 only tests them for truth), so a host
+ * that stages them may pack them -- numpy.packbits(mask, bitorder='little') over the flattened [B][H][W] array: pixel i
+ * is bit (i & 7) of byte (i >> 3) -- and expand them on the device: mask[i] = 0 / 1 for i < n_pixels. */
+int posefit_unpack_mask(const uint8_t* bits, long long n_pixels, uint8_t* mask, void* stream);
+
 /* Tracker graph edges from pose tensors: GraphDataset.get_edge_data and
  * get_edge_data_office (Tracking/datasets/graph_dataset.py:30-199, :232-330), batched over
  * n_sequences sequences of n_frames frames each.  Nodes are the detections in (sequence, frame)

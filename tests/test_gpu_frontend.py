@@ -289,3 +289,33 @@ def test_head_fed_fit_equals_resample_then_fit(pf):
             assert float((x - y).abs().max()) <= 2e-6 * max(float(y.abs().max()), 1.0)
         for x, y in zip(a[5:], c[5:]):
             assert float((x - y).abs().max()) <= 1e-4 * float(y.abs().max()), (h, w, float((x - y).abs().max()), float(y.abs().max()))
+
+
+@pytest.mark.gpu
+def test_bit_packed_masks_expand_to_the_byte_masks(pf):
+    """The one-bit-per-pixel wire format (pf.pack_mask on the host, posefit_unpack_mask on the device) against
+    numpy.unpackbits, on aligned and unaligned pixel counts and an output that is not 8-byte aligned."""
+    rng = np.random.default_rng(77)
+    for shape in [(5, 64, 64), (3, 7, 9), (1, 1, 1), (2, 33, 5), (40, 112, 112)]:
+        m = (rng.random(shape) < 0.6)
+        bits = pf.pack_mask(m)
+        assert bits.numel() == (m.size + 7) // 8
+        out = pf.unpack_mask(bits.cuda(), shape)
+        assert out.dtype == torch.uint8 and tuple(out.shape) == shape
+        assert np.array_equal(out.cpu().numpy(), m.astype(np.uint8))
+    # an unaligned destination takes the byte path: expand into an offset view through the C ABI directly
+    m = rng.random(1003) < 0.5
+    bits = pf.pack_mask(m).cuda()
+    buf = torch.full((1003 + 16,), 7, dtype=torch.uint8, device='cuda')
+    lib = pf._lib.lib()
+    code = lib.posefit_unpack_mask(bits.data_ptr(), 1003, buf.data_ptr() + 3, torch.cuda.current_stream().cuda_stream)
+    assert code == 0
+    torch.cuda.synchronize()
+    got = buf.cpu().numpy()
+    assert np.array_equal(got[3:1006], m.astype(np.uint8)) and (got[:3] == 7).all() and (got[1006:] == 7).all()
+    # the fit on an unpacked mask is the fit on the byte mask
+    d = pf.synth.make_objects(6, 64, 64, seed=91)
+    t = {k: d[k].cuda() for k in ('noc', 'depth', 'mask', 'bbox_xy0')}
+    a = pf.pose_fit_raw(t['noc'], t['depth'], t['mask'], t['bbox_xy0'])
+    b = pf.pose_fit_raw(t['noc'], t['depth'], pf.unpack_mask(pf.pack_mask(d['mask']).cuda(), d['mask'].shape), t['bbox_xy0'])
+    assert torch.equal(a.pose, b.pose) and torch.equal(a.status, b.status)
