@@ -44,6 +44,7 @@ struct CropShared {                 // lives at off_stats
   float pass2_f, band_rel;
   int n_valid, first_px, winner, first_is_inlier;
   int n_band;                       // entries in the guard-band queue
+  int stopped;                      // the winner ended the search early (pose_utils.py:80-81); 2 = its interval straddles StopT
   uint16_t spx[8][32];              // per warp: pixel of every sample of the hypothesis being fitted in double
 };
 
@@ -500,6 +501,7 @@ __global__ void __launch_bounds__(NT, 3) fit_ransac_crop_kernel(const FwdParams 
         sh->winner = -1;
         sh->first_is_inlier = 0;
         sh->n_band = 0;
+        sh->stopped = 0;
       }
     } else if (warp == NT / 32 - 1) {
       if (lane == 0) {
@@ -566,6 +568,7 @@ __global__ void __launch_bounds__(NT, 3) fit_ransac_crop_kernel(const FwdParams 
     double hi_min = __longlong_as_double(0x7ff0000000000000LL);
     float R32[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f}, T32[12], rho32 = 0.f, s32 = 1.f;
     bool have32 = false;                                         // R32 / T32 belong to hypothesis `tid` (n_hyp <= NT)
+    float hi32 = __int_as_float(0x7f800000);                     // upper end of its residual interval, rounded up
 #pragma unroll
     for (int i = 0; i < 12; ++i) T32[i] = 0.f;
     if (N > 0) {
@@ -619,6 +622,7 @@ __global__ void __launch_bounds__(NT, 3) fit_ransac_crop_kernel(const FwdParams 
         if (hi < hi_min) hi_min = hi;
         if (p.n_hyp <= NT) {
           have32 = sf.rho < 1e30f;
+          hi32 = __double2float_ru(hi);
           rho32 = sf.rho;
           s32 = sf.s;
 #pragma unroll
@@ -656,6 +660,9 @@ __global__ void __launch_bounds__(NT, 3) fit_ransac_crop_kernel(const FwdParams 
       // in the guard band.  band_rel covers float(T) against the double fit: |d r| <= s rho (|x| <= 0.87) + |dt|.
       if (my_cands != 0) {
         sh->winner = tid;
+        // did it stop the search (residual < StopT)?  Known from the interval unless that straddles StopT (then the
+        // double fit below decides)
+        sh->stopped = ((double)hi32 < stop2) ? 1 : (((double)slo[tid] >= stop2) ? 0 : 2);
         const float pass_t = (float)sh->pass_t;
         const float amx = fabsf(T32[9]) + fabsf(T32[10]) + fabsf(T32[11]);
         const float dr = have32 ? (fabsf(s32) * rho32 * 1.8f + 8.f * kScreenEps * (amx + 1.f)) : 1e30f;
@@ -670,12 +677,15 @@ __global__ void __launch_bounds__(NT, 3) fit_ransac_crop_kernel(const FwdParams 
       }
       __syncthreads();
       win = sh->winner;
-      float_pass = sh->band_rel < 0.05f;                          // an unusable / sloppy float fit: take the exact path
+      float_pass = sh->band_rel < 0.05f && sh->stopped != 2;      // an unusable / sloppy float fit: take the exact path
       // the winner's sample pixels, resolved now: the inlier pass reuses the select list's memory for its queues
       if (warp == 0) {
         crop_sample_pixels(klist, bits, gidx + win * p.n_samp, p.n_samp, N, p.idx_bits, sh->spx[0]);
-        if (!float_pass)
-          crop_fit_hypothesis(snoc, sdep, rxc, ryr, sh->spx[0], sh, red, sh->wtf, p.n_samp, P, p.W, p.w_magic, p.ref_compat);
+        if (!float_pass) {
+          const double r2w = crop_fit_hypothesis(snoc, sdep, rxc, ryr, sh->spx[0], sh, red, sh->wtf, p.n_samp, P, p.W,
+                                                 p.w_magic, p.ref_compat);
+          if (lane == 0 && sh->stopped == 2) sh->stopped = (r2w < stop2) ? 1 : 0;
+        }
       }
       __syncthreads();                                            // (the select list is free from here on)
     } else if (n_cand > 0) {
@@ -730,6 +740,7 @@ __global__ void __launch_bounds__(NT, 3) fit_ransac_crop_kernel(const FwdParams 
         if (hh.y < stop_h) { stop_h = hh.y; stop_w = w; }
       }
       win = (stop_h != 0x7fffffff) ? stop_h : (best_h != 0x7fffffff ? best_h : -1);
+      if (tid == 0) sh->stopped = (stop_h != 0x7fffffff) ? 1 : 0;
       const int win_w = (stop_h != 0x7fffffff) ? stop_w : best_w;
       if (win >= 0 && tid < 12) sh->wtf[tid] = kept[win_w * 12 + tid];
       __syncthreads();
@@ -821,6 +832,8 @@ __global__ void __launch_bounds__(NT, 3) fit_ransac_crop_kernel(const FwdParams 
         rec[19] = sh->pass_t;
         rec[20] = (double)win;
         rec[21] = (win >= 0) ? 1.0 : 0.0;
+        // iterations the reference's loop runs (= 10 np.random draws each): up to and including the one that stops it
+        rec[22] = (N > 0) ? (double)((sh->stopped == 1 && win >= 0) ? win + 1 : p.n_hyp) : 0.0;
       }
     }
     __syncthreads();                                              // stage, mom and sh are free again

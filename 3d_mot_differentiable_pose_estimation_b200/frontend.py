@@ -9,6 +9,7 @@ from __future__ import annotations
 
 from typing import NamedTuple, Optional
 
+import numpy as np
 import torch
 
 from . import _lib
@@ -52,7 +53,6 @@ def gather_crops(depth_frames, inst_masks, boxes_xyxy, frame_of: Optional[torch.
 def pack_mask(mask) -> torch.Tensor:
     """Host side of the one-bit-per-pixel wire format: mask (bool / 0-1 array or CPU tensor of any shape) ->
     uint8 CPU tensor of ceil(numel / 8) bytes, pixel i = bit (i & 7) of byte (i >> 3) over the flattened array."""
-    import numpy as np
     arr = mask.detach().cpu().numpy() if isinstance(mask, torch.Tensor) else np.asarray(mask)
     return torch.from_numpy(np.packbits(arr.reshape(-1) != 0, bitorder='little'))
 
@@ -155,7 +155,6 @@ def _prepare(pred_nocs, depth_frames, inst_masks, boxes, frame_of, campose, kinv
 
 def _draw_sample_idx(counts, n_iterations: int, n_samples: int) -> torch.Tensor:
     """The reference's draws (pose_utils.py:73), instance after instance, nothing for an empty instance."""
-    import numpy as np
     idx = np.zeros((len(counts), n_iterations, n_samples), dtype=np.int32)
     for i, n in enumerate(counts):
         if n > 0:
@@ -163,13 +162,41 @@ def _draw_sample_idx(counts, n_iterations: int, n_samples: int) -> torch.Tensor:
     return torch.from_numpy(idx)
 
 
+def _fit_on_reference_stream(counts, n_iterations: int, n_samples: int, run):
+    """Fit with np.random draws and leave the global stream where the reference's per-instance loop leaves it.
+
+    The reference draws inside getRANSACInliers' loop and stops drawing at the early-stop break (pose_utils.py:73,
+    :80-81), so the stream position of instance i+1 depends on how many iterations instance i ran.  Draw for every
+    instance assuming no early stop (true for all but near-perfect objects), fit, read back the iterations each fit says
+    the reference would have run; if an instance stopped early, replay the stream from the state before the first draw
+    -- instances up to it consume exactly their iterations, the later ones are drawn afresh -- and fit again.
+    run(sample_idx [B,n_it,n_s] CPU int32) -> (result, iterations [B] numpy int)."""
+    counts = np.asarray(counts)
+    state0 = np.random.get_state()
+    idx = _draw_sample_idx(counts, n_iterations, n_samples)
+    assumed = np.where(counts > 0, n_iterations, 0)
+    while True:
+        out, iters = run(idx)
+        late = np.nonzero((counts > 0) & (np.asarray(iters) != assumed))[0]
+        if late.size == 0:
+            return out
+        k = int(late[0])
+        assumed[k] = int(iters[k])
+        assumed[k + 1:] = np.where(counts[k + 1:] > 0, n_iterations, 0)
+        np.random.set_state(state0)
+        rows = idx.numpy()
+        for i, n in enumerate(counts):
+            if n > 0 and assumed[i] > 0:
+                rows[i, :assumed[i]] = np.random.randint(int(n), size=(int(assumed[i]), n_samples))
+
+
 def _fit(noc, crops, mask, kinv, campose, cam_index, sample_idx, ransac, bits=False):
     from .function import PoseFitFull, PoseFitRaw, pose_epilogue, REF_COMPAT, SAMPLES_ARE_BITS
     # one forward feeds both autograd (the reference detaches here, postprocess.py:151; we do not have to) and the epilogue
-    scale, rot, trans, inl, status, n_valid, pose64, winner = PoseFitFull.apply(
+    scale, rot, trans, inl, status, n_valid, pose64, winner, ctx64 = PoseFitFull.apply(
         noc, crops.depth, mask, crops.bbox_xy0, kinv, sample_idx if ransac else None, 1.0,
         REF_COMPAT | (SAMPLES_ARE_BITS if bits else 0))
-    raw = PoseFitRaw(pose64, None, status, n_valid, inl if ransac else None, winner if ransac else None)
+    raw = PoseFitRaw(pose64, ctx64, status, n_valid, inl if ransac else None, winner if ransac else None)
     epi = pose_epilogue(raw, crops.depth, mask, crops.bbox_xy0, kinv, campose=campose, cam_index=cam_index)
     return BatchedPoses(epi.global_rot, epi.global_trans, epi.global_scale, epi.euler, epi.world_box, status,
                         scale, rot, trans, raw, noc, crops, mask)
@@ -198,9 +225,11 @@ def run_pose_batched(pred_nocs, depth_frames, inst_masks, boxes_xyxy, frame_of: 
     that `randint` needs.  sample_idx='device' removes that round trip too: the draws are made on the GPU (torch's
     Philox generator, `generator=`) as uniform 32-bit values that the kernels map to floor(u N / 2^32) once they know N
     -- an opt-in, NOT numpy's stream.  Early stop and the global stream: the reference draws 10 indices per iteration
-    and stops drawing at its early-stop break (pose_utils.py:73-81), while this function (like the per-instance drop-ins)
-    draws all n_iterations x n_samples up front; after an early stop -- total residual below PassT / 100, i.e. a
-    near-perfect object -- the global np.random stream is therefore ahead of where the reference would leave it.
+    and stops drawing at its early-stop break (pose_utils.py:73-81).  The indices here are drawn up front, but the fit
+    reports how many iterations the reference would have run; after an early stop -- total residual below PassT / 100,
+    i.e. a near-perfect object -- the stream is replayed so that every later instance draws from the position the
+    reference would draw from, and the call leaves np.random where the reference's loop leaves it
+    (`_fit_on_reference_stream`; one extra fit per early-stopping instance, none otherwise).
     Instances are padded to one H x W (default: the largest box, width rounded up to 4).
 
     bucket=k: boxes of very different sizes make that padding the dominant traffic (a 24x24 box on a 160x200 canvas
@@ -230,8 +259,12 @@ def run_pose_batched(pred_nocs, depth_frames, inst_masks, boxes_xyxy, frame_of: 
         from .function import device_sample_bits
         sample_idx = device_sample_bits(int(mask.shape[0]), n_iterations, n_samples, mask.device, generator)
     if ransac and sample_idx is None:
-        counts = ((mask != 0) & (crops.depth > 0)).flatten(1).sum(1).cpu().numpy()     # the one host round trip
-        sample_idx = _draw_sample_idx(counts, n_iterations, n_samples)
+        counts = ((mask != 0) & (crops.depth > 0)).flatten(1).sum(1).cpu().numpy()     # host round trip: randint needs N
+
+        def run(idx):
+            out = _fit(noc, crops, mask, kinv, campose, cam_index, idx, ransac, False)
+            return out, out.raw.ctx[:, 30].cpu().numpy().astype(np.int64)              # iterations the reference runs
+        return _fit_on_reference_stream(counts, n_iterations, n_samples, run)
     return _fit(noc, crops, mask, kinv, campose, cam_index, sample_idx, ransac, bits)
 
 
@@ -273,15 +306,25 @@ def _run_pose_bucketed(pred_nocs, depth_frames, inst_masks, boxes, frame_of, cam
                                                take(frame_of, idx), campose, k_g, take(gt_boxes, idx),
                                                apply_statistical_filter, gh, gw)
         prepared.append((idx, k_g, crops, noc, mask, cam_index))
+    def fit_groups(sidx):
+        sidx = None if sidx is None else torch.as_tensor(sidx).to(dev)
+        return [_fit(noc, crops, mask, k_g, campose, cam_index, sidx[idx] if ransac else None, ransac, bits)
+                for idx, k_g, crops, noc, mask, cam_index in prepared]
+
     if ransac and sample_idx is None:
         counts = torch.zeros(b, dtype=torch.long, device=dev)
         for idx, _, crops, _, mask, _ in prepared:
             counts[idx] = ((mask != 0) & (crops.depth > 0)).flatten(1).sum(1)
-        sample_idx = _draw_sample_idx(counts.cpu().numpy(), n_iterations, n_samples)     # the one host round trip
-    if sample_idx is not None:
-        sample_idx = torch.as_tensor(sample_idx).to(dev)
-    parts = [_fit(noc, crops, mask, k_g, campose, cam_index, sample_idx[idx] if ransac else None, ransac, bits)
-             for idx, k_g, crops, noc, mask, cam_index in prepared]
+
+        def run(sidx):
+            parts = fit_groups(sidx)
+            iters = torch.zeros(b, dtype=torch.float64, device=dev)
+            for pr, q in zip(prepared, parts):
+                iters[pr[0]] = q.raw.ctx[:, 30]
+            return parts, iters.cpu().numpy().astype(np.int64)
+        parts = _fit_on_reference_stream(counts.cpu().numpy(), n_iterations, n_samples, run)   # host round trip: randint needs N
+    else:
+        parts = fit_groups(sample_idx)
     order = torch.cat([pr[0] for pr in prepared]) if prepared else torch.zeros(0, dtype=torch.long, device=dev)
     inv = torch.argsort(order)
 

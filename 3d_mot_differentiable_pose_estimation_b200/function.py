@@ -38,6 +38,14 @@ class PoseFitRaw(NamedTuple):
     winner: Optional[torch.Tensor]        # [B] i32 (RANSAC only)
 
 
+def ransac_iterations(raw: "PoseFitRaw") -> torch.Tensor:
+    """[B] int64: how many iterations of getRANSACInliers' loop (PoseEst/pose_utils.py:72-82) the reference would have
+    run for each object -- up to and including the one whose residual falls below StopT (:80-81), n_hyp when none does,
+    0 for an object without correspondences.  Each iteration is one `np.random.randint(N, size=10)` (:73): this is what
+    the drop-ins use to leave the global stream where the reference leaves it."""
+    return raw.ctx[:, 30].to(torch.int64)
+
+
 def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else t.data_ptr()
 
@@ -107,6 +115,11 @@ def pose_fit_raw(noc, depth, mask, bbox_xy0, kinv=None, sample_idx=None, ratio_a
     """Forward only, float64 records, no autograd.  Inputs: noc [B,3,H,W] f32 in [0,1],
     depth [B,H,W] f32, mask [B,H,W] u8/bool, bbox_xy0 [B,2] i32 (x0, y0 of each crop in the frame),
     kinv [3,3] or [B,3,3] f64 (None = MOTFront camera), sample_idx [B,n_hyp,n_samp] i32 or None.
+    Nothing here touches the host when the tensors are already what the kernels take -- CUDA, contiguous, kinv float64
+    (or None: cached per device), sample_idx int32 ON THE DEVICE; then the call is asynchronous and graph-capturable.
+    A CPU `sample_idx` (or any tensor of another dtype) is converted and uploaded on every call: that is a host-to-device
+    copy per call, not capturable -- draw on the host once per batch and pass the device tensor, or use
+    `device_sample_bits` (draws made on the GPU).
     `_f32` = (scale[B], rot[B,9], trans[B,3]) float32 tensors and `_valid_mask` [B,H,W] u8 are filled by the kernels
     when given (the autograd operator's outputs; posefit_forward_ex / posefit_forward_ransac_ex)."""
     lib = _lib.lib()
@@ -463,7 +476,8 @@ def pose_fit_head(noc_head, roi_hw, depth, mask, bbox_xy0, kinv=None):
 class PoseFitFull(torch.autograd.Function):
     """PoseFit that also hands out the float64 pose records and the RANSAC winners (non-differentiable), for
     callers that feed both autograd (scale, R, t) and the batched epilogue (records): one forward, not two.
-    Returns (scale, R, t, inlier_mask, status, n_valid, pose64 [B,16], winner [B] or empty)."""
+    Returns (scale, R, t, inlier_mask, status, n_valid, pose64 [B,16], winner [B] or empty, ctx64 [B,32]);
+    ctx64[:, 30] = RANSAC iterations the reference's loop would have run (`ransac_iterations`)."""
 
     @staticmethod
     def forward(ctx, noc, depth, mask, bbox_xy0, kinv=None, sample_idx=None, ratio_adapt=1.0, ref_compat=True,
@@ -471,8 +485,8 @@ class PoseFitFull(torch.autograd.Function):
         scale, rot, trans, inl, raw = _forward_outputs(ctx, noc, depth, mask, bbox_xy0, kinv, sample_idx, ratio_adapt,
                                                        ref_compat, return_mask)
         winner = raw.winner if raw.winner is not None else torch.empty(0, dtype=torch.int32, device=noc.device)
-        ctx.mark_non_differentiable(*[t for t in (inl, raw.status, raw.n_valid, raw.pose, winner) if t is not None])
-        return scale, rot, trans, inl, raw.status, raw.n_valid, raw.pose, winner
+        ctx.mark_non_differentiable(*[t for t in (inl, raw.status, raw.n_valid, raw.pose, winner, raw.ctx) if t is not None])
+        return scale, rot, trans, inl, raw.status, raw.n_valid, raw.pose, winner, raw.ctx
 
     @staticmethod
     def backward(ctx, g_scale, g_rot, g_trans, *_unused):

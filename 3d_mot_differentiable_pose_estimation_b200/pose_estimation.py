@@ -14,7 +14,9 @@ import numpy as np
 import torch
 
 from . import _lib
-from .function import pose_fit_raw, default_kinv, clip_mask_to_box, statistical_outlier_mask, _ptr, _stream
+from .pose_utils import rewind_to_reference_stream
+from .function import (pose_fit_raw, default_kinv, clip_mask_to_box, statistical_outlier_mask, ransac_iterations,
+                       _ptr, _stream)
 
 __all__ = ['backproject', 'transform_pc', 'cam2world', 'sort_bbox', 'run_pose', 'run_pose_office']
 
@@ -139,8 +141,10 @@ def _run(nocs, depth, kinv, campose, bin_mask, abs_bbox, use_depth_box, gt_3d_bo
     n = int(dst.shape[0])
     if n == 0:                                                          # :361-362
         return None, None, None, None, None, None
+    rng_state = np.random.get_state()
     idx = np.random.randint(n, size=(N_ITERATIONS, N_SAMPLES))          # pose_utils.py:73
     raw = pose_fit_raw(noc, d, m, xy0, kinv, sample_idx=torch.from_numpy(idx.astype(np.int32))[None])
+    rewind_to_reference_stream(rng_state, n, int(ransac_iterations(raw)[0]), N_ITERATIONS)   # :80-81 stops the draws too
     status = int(raw.status[0])
     pose = raw.pose[0].cpu().numpy()
     if status == 2:

@@ -11,7 +11,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .function import points_fit_raw, _ptr, _stream
+from .function import points_fit_raw, ransac_iterations, _ptr, _stream
 
 __all__ = ['evaluateModel', 'estimateSimilarityUmeyama', 'getRANSACInliers', 'estimateSimilarityTransform']
 
@@ -78,10 +78,24 @@ def evaluateModel(OutTransform, SourceHom, TargetHom, PassThreshold):
 def _ransac(SourceHom, TargetHom, n_iter, pass_t, stop_t, ratio_adapt=1.0):
     src, dst = _planes(SourceHom), _planes(TargetHom)
     n = int(src.shape[2])
+    state = np.random.get_state()
     idx = np.random.randint(n, size=(n_iter, N_SAMPLES))  # :73 -- drawn up front from the same global RNG
     raw = points_fit_raw(src, dst, sample_idx=torch.from_numpy(idx.astype(np.int32))[None], ratio_adapt=ratio_adapt,
                          pass_threshold=pass_t, stop_threshold=stop_t)
+    rewind_to_reference_stream(state, n, int(ransac_iterations(raw)[0]), n_iter)
     return raw
+
+
+def rewind_to_reference_stream(state, n_points: int, iterations_run: int, n_iter: int, n_samples: int = N_SAMPLES):
+    """The reference draws `np.random.randint(N, size=10)` INSIDE its loop and stops drawing when the loop breaks
+    (pose_utils.py:73, :80-81); the drop-ins draw every iteration's indices up front.  After an early stop put the global
+    stream where the reference leaves it: back to `state` (taken before the draw), then exactly the draws of the
+    iterations that ran.  (Legacy `randint` produces its values one after another from the bit stream, so one call of
+    `iterations_run` x 10 consumes what `iterations_run` calls of 10 consume; tests/golden/rng_stream.npz pins it.)"""
+    if 0 <= iterations_run < n_iter:
+        np.random.set_state(state)
+        if iterations_run > 0:
+            np.random.randint(n_points, size=(iterations_run, n_samples))
 
 
 def getRANSACInliers(SourceHom, TargetHom, MaxIterations=100, PassThreshold=200, StopThreshold=1):

@@ -135,8 +135,11 @@ def ransac_inliers(src, dst, sample_idx, pass_t, stop_t):
     margin = np.inf
     if best_r is not None and pass_t > 0 and np.isfinite(pass_t):
         margin = float(np.min(np.abs(best_r - pass_t)) / pass_t)
+    # iterations the loop ran (each one np.random.randint(N, size=10) in the reference, :73): residuals stay NaN
+    # behind the early stop
+    iterations = int(np.count_nonzero(~np.isnan(residuals))) if np.isnan(residuals).any() else int(sample_idx.shape[0])
     return dict(inlier_idx=best_idx, ratio=best_ratio, winner=best_h, residuals=residuals,
-                best_residual=best_res, margin=margin)
+                best_residual=best_res, margin=margin, iterations=iterations)
 
 
 def pass_thresholds(src, dst, ratio_adapt=1.0):
@@ -210,10 +213,10 @@ def pose_from_correspondences(noc_pts, depth_pts, sample_idx=None, ratio_adapt=1
     except RuntimeError:
         return dict(status=3, n_valid=n)
     if not res['ok']:
-        return dict(status=2, n_valid=n, **{k: res[k] for k in ('inlier_idx', 'ratio', 'winner', 'margin', 'pass_t')})
+        return dict(status=2, n_valid=n, **{k: res[k] for k in ('inlier_idx', 'ratio', 'winner', 'margin', 'pass_t', 'iterations')})
     out = dict(status=0, n_valid=n, s=float(res['scales'][0]), rot_t=res['rot_t'], R=res['rot_t'].T,
                t=res['trans'])
-    for k in ('inlier_idx', 'ratio', 'winner', 'margin', 'pass_t', 'residuals'):
+    for k in ('inlier_idx', 'ratio', 'winner', 'margin', 'pass_t', 'residuals', 'iterations'):
         if k in res:
             out[k] = res[k]
     return out

@@ -49,8 +49,10 @@ def replay(idx):
     real = np.random.randint
 
     def fake(high, size=None, **kw):
-        assert tuple(size) == idx.shape and idx.max() < high
-        return idx.copy()
+        # the up-front draw of every iteration, or -- after an early stop -- the drop-in's replay of the iterations
+        # that ran (pose_utils.rewind_to_reference_stream): a prefix of the same rows
+        assert tuple(size)[1:] == idx.shape[1:] and size[0] <= idx.shape[0] and idx.max() < high
+        return idx[:size[0]].copy()
 
     np.random.randint = fake
     try:
@@ -112,6 +114,33 @@ def test_estimateSimilarityTransform(pf, golden_dir, monkeypatch, capsys):
         assert rot_err_deg(rot, g[f'rotation_{k}']) < 1e-6, name
         np.testing.assert_allclose(scales, g[f'scales_{k}'], rtol=1e-9, err_msg=name)
         np.testing.assert_allclose(trans, g[f'translation_{k}'], rtol=1e-9, atol=1e-9, err_msg=name)
+
+
+def test_drop_ins_leave_np_random_where_the_reference_leaves_it(pf, golden_dir):
+    """tests/golden/rng_stream.npz: the real estimateSimilarityTransform on a seeded, unpatched global stream.  The
+    reference draws inside its RANSAC loop and stops drawing at the early stop (pose_utils.py:73, :80-81); the drop-in
+    draws up front and then rewinds by the iterations the kernel reports: same outputs, same iteration count, and the
+    NEXT values of np.random are the reference's."""
+    g = np.load(os.path.join(golden_dir, 'rng_stream.npz'))
+    seen = set()
+    for name in [str(n) for n in g['names']]:
+        src, dst = g[name + '_src'], g[name + '_dst']
+        seed, ra, iters = int(g[name + '_seed']), float(g[name + '_ratio_adapt']), int(g[name + '_iterations'])
+        seen.add(iters)
+        np.random.seed(seed)
+        scales, rot, trans, tf = pf.pose_utils.estimateSimilarityTransform(src, dst, ratio_adapt=ra)
+        nxt = np.random.randint(2 ** 31 - 1, size=4)
+        assert np.array_equal(nxt, g[name + '_next']), (name, iters)
+        assert rot_err_deg(rot, g[name + '_rotation']) < 1e-6, name
+        np.testing.assert_allclose(scales, g[name + '_scales'], rtol=1e-9, err_msg=name)
+        np.testing.assert_allclose(trans, g[name + '_translation'], rtol=1e-9, atol=1e-9, err_msg=name)
+        # the raw entry reports the iteration count itself
+        np.random.seed(seed)
+        idx = torch.from_numpy(np.random.randint(src.shape[0], size=(100, 10)).astype(np.int32))[None].cuda()
+        planes = lambda a: torch.from_numpy(np.ascontiguousarray(a.T))[None].cuda()    # noqa: E731  [1,3,N]
+        raw = pf.points_fit_raw(planes(src), planes(dst), sample_idx=idx, ratio_adapt=ra)
+        assert int(pf.ransac_iterations(raw)[0]) == iters, name
+    assert 100 in seen and 1 in seen and len(seen) >= 4          # no stop, stop at once, stops in the middle
 
 
 @pytest.mark.parametrize('tag,h,w,b', [('small', 24, 32, 6), ('odd', 19, 27, 4)])

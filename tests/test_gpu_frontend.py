@@ -166,6 +166,84 @@ def test_run_pose_batched_equals_per_instance_drop_in(pf):
     assert int(out.status[4]) == 1
 
 
+def test_run_pose_batched_follows_the_reference_stream_after_an_early_stop(pf):
+    """An instance whose first hypothesis already scores below StopT ends the reference's RANSAC loop -- and its
+    np.random draws -- after ONE iteration (pose_utils.py:73, :80-81), so every later instance draws from an earlier
+    stream position than an up-front draw of 100 x 10 per instance would give it.  run_pose_batched and the per-instance
+    drop-in both follow that: same poses, same iteration counts, and np.random ends where the lazy draws end."""
+    rng = np.random.default_rng(18)
+    gen = torch.Generator().manual_seed(18)
+    FH, FW = 240, 320
+    boxes = np.array([[40, 30, 100, 94], [150, 60, 178, 88], [10, 150, 60, 214], [200, 120, 264, 180]], dtype=np.int32)
+    b = boxes.shape[0]
+    frame_of = np.zeros(b, dtype=np.int32)
+    head = torch.rand(b, 3, 28, 28, generator=gen)
+    depth = np.zeros((1, FH, FW), dtype=np.float32)
+    masks = np.zeros((b, FH, FW), dtype=bool)
+    kinv = np.linalg.inv(po.motfront_intrinsics())
+    for i in range(b):
+        x0, y0, x1, y1 = boxes[i]
+        h, w = y1 - y0, x1 - x0
+        if i == 1:
+            # 28 x 28 box: roi_align of the 28 x 28 head is the identity, so the head IS the NOC patch.  Exact similarity
+            # with identity rotation (SURVEY.md F3: only those score ~0): noc = (p - t) / s + 0.5 for the back-projected p
+            vv, uu = np.meshgrid(np.arange(y0, y1), np.arange(x0, x1), indexing='ij')
+            z = (3.0 + 0.2 * np.sin(uu / 5.0) + 0.1 * np.cos(vv / 7.0)).astype(np.float32)
+            rays = np.stack([uu, vv, np.ones_like(uu)], axis=-1).astype(np.float64) @ kinv.T
+            pts = rays * z[..., None].astype(np.float64) * np.array([1.0, -1.0, -1.0])       # pose_estimation.py:34-41
+            noc = (pts - np.array([0.1, -0.2, -3.0])) / 2.0 + 0.5
+            head[i] = torch.from_numpy(noc).permute(2, 0, 1).to(torch.float32)
+            m = np.ones((h, w), dtype=bool)
+        else:
+            patch = _reference_patch(head[i], h, w).permute(1, 2, 0).numpy().astype(np.float64)
+            rot = np.linalg.qr(rng.normal(size=(3, 3)))[0]
+            rot *= np.sign(np.linalg.det(rot))
+            pts = 1.5 * (patch.reshape(-1, 3) - 0.5) @ rot.T + np.array([0.0, 0.0, -3.5])
+            z = ((-pts[:, 2]).reshape(h, w) + rng.normal(scale=0.01, size=(h, w))).astype(np.float32)
+            m = rng.uniform(size=(h, w)) < 0.8
+        depth[0, y0:y1, x0:x1] = z
+        masks[i, y0:y1, x0:x1] = m
+    campose = np.identity(4)
+    campose[:3, :3] = np.linalg.qr(rng.normal(size=(3, 3)))[0]
+    campose[:3, 3] = rng.normal(size=3)
+
+    np.random.seed(4321)
+    out = pf.run_pose_batched(head.cuda(), torch.from_numpy(depth).cuda(), torch.from_numpy(masks).cuda(),
+                              torch.from_numpy(boxes).cuda(), torch.from_numpy(frame_of).cuda(),
+                              campose=torch.from_numpy(campose), apply_statistical_filter=False)
+    next_batched = np.random.randint(2 ** 31 - 1, size=4)
+    iters = pf.ransac_iterations(out.raw).cpu().numpy()
+    counts = out.raw.n_valid.cpu().numpy()
+    assert iters[1] == 1 and (np.delete(iters, 1) == 100).all(), iters
+
+    # the lazy draws of the reference, replayed: iteration count x 10 draws per instance, in instance order
+    np.random.seed(4321)
+    for i in range(b):
+        np.random.randint(int(counts[i]), size=(int(iters[i]), 10))
+    assert np.array_equal(np.random.randint(2 ** 31 - 1, size=4), next_batched)
+
+    # the per-instance drop-in, same seed: same stream, same poses
+    monkey = pf.pose_estimation.APPLY_STATISTICAL_FILTER
+    pf.pose_estimation.APPLY_STATISTICAL_FILTER = False
+    try:
+        np.random.seed(4321)
+        for i in range(b):
+            x0, y0, x1, y1 = boxes[i]
+            patch = _reference_patch(head[i], y1 - y0, x1 - x0).permute(1, 2, 0).contiguous()
+            ref = pf.pose_estimation.run_pose(patch.cuda(), depth[0], campose, torch.from_numpy(masks[i]).cuda(),
+                                              tuple(int(v) for v in boxes[i]))
+            assert ref[0] is not None and int(out.status[i]) == 0, i
+            np.testing.assert_allclose(out.global_rot[i].cpu().numpy(), ref[0], rtol=1e-5, atol=1e-6)
+            np.testing.assert_allclose(out.global_trans[i].cpu().numpy(), ref[1], rtol=1e-5, atol=1e-6)
+            np.testing.assert_allclose(float(out.global_scale[i]), ref[2], rtol=1e-5)
+        assert np.array_equal(np.random.randint(2 ** 31 - 1, size=4), next_batched)
+    finally:
+        pf.pose_estimation.APPLY_STATISTICAL_FILTER = monkey
+    # the early stopper recovered its similarity: scale 2, identity rotation
+    np.testing.assert_allclose(float(out.scale[1]), 2.0, rtol=1e-5)
+    np.testing.assert_allclose(out.rot[1].cpu().numpy(), np.identity(3), atol=1e-5)
+
+
 def test_run_pose_batched_is_differentiable_to_the_head_output(pf):
     """Gradients of a pose loss reach the NOC head output through the fit and the resample -- the end-to-end
     path the reference cuts at postprocess.py:151 -- and equal the explicit composition resample -> pose_fit."""

@@ -156,3 +156,24 @@ def test_sort_bbox_matches_reference(golden_dir):
     for k in range(n):
         got = drop_in.sort_bbox(g[f'in_{k}'].copy())
         np.testing.assert_array_equal(got, g[f'out_{k}'], err_msg=str(g[f'tag_{k}']))
+
+
+def test_rng_stream_position_matches_reference(golden_dir):
+    """tests/golden/rng_stream.npz (oracle/gen_golden_rng.py: the real estimateSimilarityTransform on a seeded, UNPATCHED
+    global stream): the oracle, fed with the draws made up front from the same seed, reproduces the outputs and the
+    number of loop iterations; and rewinding to the seed and drawing iterations x 10 leaves np.random exactly where
+    the reference's lazy per-iteration draws left it (the next four values of the stream)."""
+    g = np.load(os.path.join(golden_dir, 'rng_stream.npz'))
+    for name in [str(n) for n in g['names']]:
+        src, dst = g[name + '_src'], g[name + '_dst']
+        seed, ra, iters = int(g[name + '_seed']), float(g[name + '_ratio_adapt']), int(g[name + '_iterations'])
+        np.random.seed(seed)
+        idx = np.random.randint(src.shape[0], size=(100, 10))
+        res = po.similarity_transform(src, dst, idx, ra)
+        assert res['ok'] == bool(g[name + '_ok']), name
+        assert res['iterations'] == iters, (name, res['iterations'], iters)
+        np.testing.assert_allclose(res['out_transform'], g[name + '_transform'], rtol=1e-9, atol=1e-11, err_msg=name)
+        np.random.seed(seed)
+        if iters:
+            np.random.randint(src.shape[0], size=(iters, 10))
+        assert np.array_equal(np.random.randint(2 ** 31 - 1, size=4), g[name + '_next']), name
