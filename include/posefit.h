@@ -28,7 +28,11 @@
  *     correspondences in the final fit, [14] inlier ratio as the reference counts it
  *     (pose_utils.py:10-12, only meaningful for the RANSAC entry), [15] pass threshold PassT.
  *   - ctx[b][32] (float64): state saved for posefit_backward (R, (tr(H)I-H)^-1, H, s, var, n,
- *     mu_x, mu_y); opaque to callers.
+ *     mu_x, mu_y); opaque to callers except ctx[b][30], written by the RANSAC entries: the number of
+ *     iterations getRANSACInliers' loop would have run (pose_utils.py:72-82: up to and including the
+ *     one whose residual falls below StopT, n_hyp when none does, 0 without correspondences) -- one
+ *     np.random.randint(N, size=10) each (:73), which is what a host needs to leave the global
+ *     random stream where the reference leaves it.
  *   - status[b] (int32): 0 ok; 1 no valid correspondence (run_pose returns 6xNone,
  *     pose_estimation.py:361-362); 2 inlier ratio < 0.1 (4xNone, pose_utils.py:105-107);
  *     3 NaN covariance (RuntimeError, pose_utils.py:32-36).  For status != 0 the pose is
