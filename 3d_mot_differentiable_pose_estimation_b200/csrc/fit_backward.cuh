@@ -32,6 +32,7 @@ struct BwdParams {
   int chunk_px, chunks_per_obj;
   int vec_ok;
   int early_dep;
+  int opc;                // K-backward-coef: objects per CTA (posefit_common.cuh: solve_object)
 };
 
 struct BwdCoef {          // per-object coefficients, already scaled by 1/n
@@ -120,15 +121,18 @@ __device__ __forceinline__ void bwd_coefficients(const BwdParams& p, int obj, Bw
 // One thread per object: adjoint coefficients -> coef[B] (144 B each) in the workspace.
 __global__ void __launch_bounds__(128) fit_backward_coef_kernel(const BwdParams p) {
 #if __CUDA_ARCH__ >= 900
+  PF_TRACE_BEGIN(2);
   if (p.early_dep & 4) asm volatile("griddepcontrol.launch_dependents;");   // K-backward's CTAs queue up behind us
   asm volatile("griddepcontrol.wait;" ::: "memory");          // ctx / status come from the forward kernels
   if (!(p.early_dep & 4)) asm volatile("griddepcontrol.launch_dependents;");
 #endif
-  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  PF_TRACE_BEGIN(10);
+  const int o = solve_object(p.opc, p.B);
   if (o >= p.B) return;
   BwdCoef c;
   bwd_coefficients(p, o, c);
   p.coef[o] = c;
+  PF_TRACE_END(2);
 }
 
 struct BwdLoad {
@@ -147,11 +151,13 @@ template <int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB) fit_backward_kernel(const BwdParams p) {
   __shared__ __align__(16) BwdCoef coefs[2];
   static_assert(sizeof(BwdCoef) == 144, "coefficient record is 9 x 16 bytes");
+  PF_TRACE_BEGIN(3);
 #if __CUDA_ARCH__ >= 900
   if (p.early_dep & 8) asm volatile("griddepcontrol.launch_dependents;");   // the next call's first kernel may queue up
   asm volatile("griddepcontrol.wait;" ::: "memory");            // coefficients written by fit_backward_coef_kernel
   if (!(p.early_dep & 8)) asm volatile("griddepcontrol.launch_dependents;");
 #endif
+  PF_TRACE_BEGIN(11);
   const int tid = threadIdx.x;
   const int n_units = p.B * p.chunks_per_obj;
   auto provide = [&](int unit, int buf) {
@@ -240,6 +246,7 @@ __global__ void __launch_bounds__(NT, MINB) fit_backward_kernel(const BwdParams 
       }
     }
   }
+  PF_TRACE_END(3);
 }
 
 }  // namespace posefit

@@ -166,9 +166,11 @@ __global__ void __launch_bounds__(512, 1) fit_moments_kernel(const FwdParams p) 
   // allow) while this kernel still runs, and block in their own griddepcontrol.wait until this grid
   // has completed.  Every kernel of the chain touches global memory only after its own wait, so
   // completion order (every RAW / WAR dependence between consecutive kernels) is unchanged.
+  PF_TRACE_BEGIN(0);
   if (p.early_dep & 1) asm volatile("griddepcontrol.launch_dependents;");
   asm volatile("griddepcontrol.wait;" ::: "memory");          // inputs may come from the previous kernel in the stream
   if (!(p.early_dep & 1)) asm volatile("griddepcontrol.launch_dependents;");
+  PF_TRACE_BEGIN(8);
 #endif
   const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
   const long long c_begin = gw * p.chunks_per_warp;
@@ -351,6 +353,7 @@ __global__ void __launch_bounds__(512, 1) fit_moments_kernel(const FwdParams p) 
       if (slot == DEPTH) slot = 0;
     }
     write_part(cur_obj);
+    PF_TRACE_END(0);
     return;
   }
   if (!POINTS) {
@@ -474,6 +477,7 @@ __global__ void __launch_bounds__(512, 1) fit_moments_kernel(const FwdParams p) 
     if (++slot == DEPTH) slot = 0;
   }
   write_part(cur_obj);
+  PF_TRACE_END(0);
 }
 
 // One thread per object: merge the partial moments and solve (pose_utils.py:16-61).
@@ -490,7 +494,8 @@ __global__ void __launch_bounds__(128) fit_solve_kernel(const FwdParams p) {
 #if __CUDA_ARCH__ >= 900
   if (p.early_dep & 2) asm volatile("griddepcontrol.launch_dependents;");
 #endif
-  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  PF_TRACE_BEGIN(1);
+  const int o = solve_object(p.opc, p.B);
 #pragma unroll 1
   for (int pass = p.prewarm ? 0 : 1; pass < 2; ++pass) {
     double s[kAccPlain];
@@ -504,6 +509,7 @@ __global__ void __launch_bounds__(128) fit_solve_kernel(const FwdParams p) {
       asm volatile("griddepcontrol.wait;" ::: "memory");        // K-moments has completed and flushed
       if (!(p.early_dep & 2)) asm volatile("griddepcontrol.launch_dependents;");
 #endif
+      PF_TRACE_BOTH(9);
       if (o >= p.B) return;
       const long long c0 = (long long)o * p.chunks_per_obj;
       const long long w0 = c0 / p.chunks_per_warp, w1 = (c0 + p.chunks_per_obj - 1) / p.chunks_per_warp;
@@ -538,11 +544,18 @@ __global__ void __launch_bounds__(128) fit_solve_kernel(const FwdParams p) {
 #pragma unroll
     for (int i = 0; i < 9; ++i) mo.syx[i] = s[7 + i];
     mo.sxx = s[16];
+#ifdef PF_TRACE
+    if (pass == 1 && mo.sxx != -1.2345e300) PF_TRACE_BOTH(12);   // the merged moments are in registers
+#endif
     Fit f;
     fit_from_moments<true>(mo, f);
+#ifdef PF_TRACE
+    if (pass == 1 && f.s != -1.2345e300) PF_TRACE_BOTH(13);      // solved, nothing written yet
+#endif
     const int status = (mo.n > 0.0) ? f.status : PF_EMPTY;      // pose_estimation.py:361-362
     if (pass == 1) {
       write_pose(p, o, f, status, mo.n, 1.0, 0.0, mo.n);
+      PF_TRACE_END(1);
     } else if (f.s == -1.2345e300 && p.pose != nullptr && o < p.B) {
       p.pose[(size_t)o * POSEFIT_POSE_DOUBLES] = f.R[0] + f.t[0] + f.Linv[0] + f.H[0];   // never true: keeps the warm-up pass alive
     }

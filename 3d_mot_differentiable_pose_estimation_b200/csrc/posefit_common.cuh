@@ -103,6 +103,7 @@ struct FwdParams {
   int n_stages, tma_ok;
   int early_dep;                // bit k: kernel k of the chain signals its dependents before its own wait
   int prewarm;                  // K-solve kernels: run a warm-up pass before griddepcontrol.wait (small grids)
+  int opc;                      // K-solve kernels: objects per CTA (threads beyond it idle; see solve_object)
   int n_words;                  // ceil(P / 32)
   uint32_t w_magic;             // ceil(2^32 / W): px / W == __umulhi(px, w_magic) for px, W < 65536
   // plain path (K-moments / K-solve)
@@ -115,6 +116,15 @@ struct FwdParams {
   uint32_t off_geom, off_tables, off_red, off_bits, off_prefix, off_stats, off_res, off_tf, off_stages;
   uint32_t stage_bytes, st_depth, st_mask, st_idx;   // offsets inside one stage
 };
+
+// One-thread-per-object kernels (K-solve, K-solve-ransac, K-backward-coef): the object of this thread.  Every thread
+// reads and writes its own records element by element -- 32 different lines per warp instruction, which one SM's load /
+// store unit takes one at a time -- so small batches are spread over all SMs, `opc` objects per CTA (the first opc
+// threads; the others idle), instead of filling a few CTAs.  Returns n_objects for an idle thread.
+__device__ __forceinline__ int solve_object(int opc, int n_objects) {
+  const int o = (int)blockIdx.x * opc + (int)threadIdx.x;
+  return ((int)threadIdx.x < opc && o < n_objects) ? o : n_objects;
+}
 
 // Per-object geometry (K^-1 and the crop origin) lives in shared memory, double buffered: the
 // record of object j+1 is fetched with cp.async (LDGSTS, no register staging) while object j is
@@ -351,6 +361,26 @@ __device__ __forceinline__ void block_reduce(double (&v)[N], double* red, double
     out[tid] = s;
   }
 }
+
+// Debug build only (make trace): wall-clock span of every kernel of the plain path -- earliest start and latest end over
+// its warps (%globaltimer, ns) -- read back through posefit_debug_trace (tools/trace_step.py).
+// ids: 0 moments, 1 solve, 2 backward coefficients, 3 backward; 8 + id = the same kernel after its griddepcontrol.wait;
+// 12 / 13 = solve kernel: moments merged / solved.
+#ifdef PF_TRACE
+__device__ unsigned long long g_trace[32];
+__device__ __forceinline__ unsigned long long pf_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define PF_TRACE_BEGIN(k) do { if ((threadIdx.x & 31) == 0) atomicMin(&g_trace[2 * (k)], pf_now()); } while (0)
+#define PF_TRACE_END(k) do { if ((threadIdx.x & 31) == 0) atomicMax(&g_trace[2 * (k) + 1], pf_now()); } while (0)
+#define PF_TRACE_BOTH(k) do { PF_TRACE_BEGIN(k); PF_TRACE_END(k); } while (0)   /* earliest and latest warp at a point */
+#else
+#define PF_TRACE_BEGIN(k) do { } while (0)
+#define PF_TRACE_END(k) do { } while (0)
+#define PF_TRACE_BOTH(k) do { } while (0)
+#endif
 
 // Write one object's outputs (include/posefit.h: pose[16], ctx[32], status, n_valid).
 __device__ __forceinline__ void write_pose(const FwdParams& p, int obj, const Fit& f, int status, double n_fit,
