@@ -495,7 +495,11 @@ __global__ void __launch_bounds__(128) fit_solve_kernel(const FwdParams p) {
   if (p.early_dep & 2) asm volatile("griddepcontrol.launch_dependents;");
 #endif
   PF_TRACE_BEGIN(1);
+  extern __shared__ __align__(16) double solve_tiles[];              // [warps of the CTA][kTileDoubles]
   const int o = solve_object(p.opc, p.B);
+  double* tile = solve_tiles + (threadIdx.x >> 5) * kTileDoubles;
+  long long row0;
+  const int n_rows = solve_warp_rows(p.opc, p.B, row0);
 #pragma unroll 1
   for (int pass = p.prewarm ? 0 : 1; pass < 2; ++pass) {
     double s[kAccPlain];
@@ -510,31 +514,34 @@ __global__ void __launch_bounds__(128) fit_solve_kernel(const FwdParams p) {
       if (!(p.early_dep & 2)) asm volatile("griddepcontrol.launch_dependents;");
 #endif
       PF_TRACE_BOTH(9);
-      if (o >= p.B) return;
-      const long long c0 = (long long)o * p.chunks_per_obj;
-      const long long w0 = c0 / p.chunks_per_warp, w1 = (c0 + p.chunks_per_obj - 1) / p.chunks_per_warp;
-      const int n_parts = (int)(w1 - w0) + 1;
-      const double* base = p.ws + (size_t)o * p.max_parts * kAccPlain;
+      if (n_rows == 0) return;                                  // (whole warps only: the copies below are the warp's)
+      // merge the partial records: four at a time (68 independent loads in flight), in order
 #pragma unroll
       for (int i = 0; i < kAccPlain; ++i) s[i] = 0.0;
+      if (o < p.B) {                                            // (an idle lane of a live warp stays an empty object)
+        const long long c0 = (long long)o * p.chunks_per_obj;
+        const long long w0 = c0 / p.chunks_per_warp, w1 = (c0 + p.chunks_per_obj - 1) / p.chunks_per_warp;
+        const int n_parts = (int)(w1 - w0) + 1;
+        const double* base = p.ws + (size_t)o * p.max_parts * kAccPlain;
 #pragma unroll 1
-      for (int k = 0; k < n_parts; k += 4) {
-        double v[4][kAccPlain];
+        for (int k = 0; k < n_parts; k += 4) {
+          double v[4][kAccPlain];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const bool on = k + u < n_parts;
-          const double* part = base + (size_t)(on ? k + u : k) * kAccPlain;
+          for (int u = 0; u < 4; ++u) {
+            const bool on = k + u < n_parts;
+            const double* part = base + (size_t)(on ? k + u : k) * kAccPlain;
 #pragma unroll
-          for (int i = 0; i < kAccPlain; ++i) v[u][i] = part[i];
-          if (!on) {
+            for (int i = 0; i < kAccPlain; ++i) v[u][i] = part[i];
+            if (!on) {
 #pragma unroll
-            for (int i = 0; i < kAccPlain; ++i) v[u][i] = 0.0;
+              for (int i = 0; i < kAccPlain; ++i) v[u][i] = 0.0;
+            }
           }
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int i = 0; i < kAccPlain; ++i) s[i] += v[u][i];
         }
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-#pragma unroll
-          for (int i = 0; i < kAccPlain; ++i) s[i] += v[u][i];
       }
     }
     Moments mo;
@@ -554,7 +561,7 @@ __global__ void __launch_bounds__(128) fit_solve_kernel(const FwdParams p) {
 #endif
     const int status = (mo.n > 0.0) ? f.status : PF_EMPTY;      // pose_estimation.py:361-362
     if (pass == 1) {
-      write_pose(p, o, f, status, mo.n, 1.0, 0.0, mo.n);
+      write_pose(p, row0, n_rows, tile, f, status, mo.n, 1.0, 0.0, mo.n);
       PF_TRACE_END(1);
     } else if (f.s == -1.2345e300 && p.pose != nullptr && o < p.B) {
       p.pose[(size_t)o * POSEFIT_POSE_DOUBLES] = f.R[0] + f.t[0] + f.Linv[0] + f.H[0];   // never true: keeps the warm-up pass alive

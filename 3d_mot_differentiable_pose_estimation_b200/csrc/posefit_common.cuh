@@ -126,6 +126,15 @@ __device__ __forceinline__ int solve_object(int opc, int n_objects) {
   return ((int)threadIdx.x < opc && o < n_objects) ? o : n_objects;
 }
 
+// first object of the calling warp and how many of its lanes hold one (0 .. 32)
+__device__ __forceinline__ int solve_warp_rows(int opc, int n_objects, long long& row0) {
+  const int w0 = (int)threadIdx.x & ~31;
+  row0 = (long long)blockIdx.x * opc + w0;
+  long long n = (long long)(opc - w0);
+  if (n > n_objects - row0) n = n_objects - row0;
+  return n < 0 ? 0 : (n > 32 ? 32 : (int)n);
+}
+
 // Per-object geometry (K^-1 and the crop origin) lives in shared memory, double buffered: the
 // record of object j+1 is fetched with cp.async (LDGSTS, no register staging) while object j is
 // being processed.
@@ -140,6 +149,13 @@ struct ObjGeom {
   int x0, y0;
   bool simple;
 };
+
+// Ask L2 for [ptr, ptr + bytes) (widened to 16-byte granules): one instruction, nothing lands in the SM.
+__device__ __forceinline__ void l2_prefetch_bulk(const void* ptr, uint32_t bytes) {
+  const uint64_t a = reinterpret_cast<uint64_t>(ptr), a0 = a & ~15ull;
+  const uint32_t n = (uint32_t)((a + bytes + 15ull - a0) & ~15ull);
+  if (n != 0u) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a0), "r"(n) : "memory");
+}
 
 __device__ __forceinline__ void cp_async_8(void* dst, const void* src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
@@ -382,9 +398,79 @@ __device__ __forceinline__ unsigned long long pf_now() {
 #define PF_TRACE_BOTH(k) do { } while (0)
 #endif
 
-// Write one object's outputs (include/posefit.h: pose[16], ctx[32], status, n_valid).
-__device__ __forceinline__ void write_pose(const FwdParams& p, int obj, const Fit& f, int status, double n_fit,
-                                           double ratio, double pass_t, double n_valid) {
+// ---- records of the one-thread-per-object kernels cross global memory through a per-warp tile ---------------------
+// A thread that reads or writes its own object's record element by element touches 32 different lines per warp
+// instruction, and an SM's load / store unit takes those one at a time (tools/trace_step.py: with 28 objects per warp
+// the solve kernel of BASELINE config 2 spent more time in its loads and stores than in the 3x3 solve).  So the warp
+// moves the records of the <= 32 consecutive objects it owns with consecutive addresses, through rows of a shared-memory
+// tile (row = object, odd stride); every thread works on its own row.
+constexpr int kTileStride = 33;
+constexpr int kTileDoubles = 32 * kTileStride;            // per warp
+
+template <typename T, int ROW, int STRIDE>
+__device__ __forceinline__ void warp_tile_store(T* g, long long row0, int n_rows, const T* tile) {
+  const int lane = threadIdx.x & 31;
+  T* dst = g + row0 * ROW;
+  for (int i = lane; i < n_rows * ROW; i += 32) dst[i] = tile[(i / ROW) * STRIDE + (i % ROW)];
+}
+
+// Write the outputs of the warp's objects row0 .. row0 + n_rows - 1 (include/posefit.h: pose[16], ctx[32], status,
+// n_valid, optional float32 copies); lane j holds object row0 + j.  Called by ALL 32 lanes (lanes >= n_rows hold
+// anything and write nothing); `tile` = this warp's kTileDoubles of shared memory.  ctx30: RANSAC iteration count.
+__device__ __forceinline__ void write_pose(const FwdParams& p, long long row0, int n_rows, double* tile, const Fit& f,
+                                           int status, double n_fit, double ratio, double pass_t, double n_valid,
+                                           double ctx30 = 0.0) {
+  const int lane = threadIdx.x & 31;
+  double* row = tile + lane * kTileStride;
+  __syncwarp();
+  row[0] = f.s;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) row[1 + i] = f.R[i];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) row[10 + i] = f.t[i];
+  row[13] = (status == PF_OK) ? n_fit : 0.0;
+  row[14] = ratio;
+  row[15] = pass_t;
+  __syncwarp();
+  warp_tile_store<double, POSEFIT_POSE_DOUBLES, kTileStride>(p.pose, row0, n_rows, tile);
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 9; ++i) row[i] = f.R[i];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) { row[9 + i] = f.Linv[i]; row[15 + i] = f.H[i]; }
+  row[21] = f.s;
+  row[22] = f.var;
+  row[23] = (status == PF_OK) ? n_fit : 0.0;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) { row[24 + i] = f.mux[i]; row[27 + i] = f.muy[i]; }
+  row[30] = ctx30;
+  row[31] = 0.0;
+  __syncwarp();
+  warp_tile_store<double, POSEFIT_CTX_DOUBLES, kTileStride>(p.ctx, row0, n_rows, tile);
+  if (lane < n_rows) {                                      // one word per object: consecutive as they are
+    p.status[row0 + lane] = status;
+    p.n_valid[row0 + lane] = (int)n_valid;
+    if (p.out_scale != nullptr) p.out_scale[row0 + lane] = (float)f.s;
+  }
+  if (p.out_rot != nullptr || p.out_trans != nullptr) {
+    float* tf = reinterpret_cast<float*>(tile);
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 9; ++i) tf[lane * 13 + i] = (float)f.R[i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) tf[lane * 13 + 9 + i] = (float)f.t[i];
+    __syncwarp();
+    if (p.out_rot != nullptr) warp_tile_store<float, 9, 13>(p.out_rot, row0, n_rows, tf);
+    if (p.out_trans != nullptr) warp_tile_store<float, 3, 13>(p.out_trans, row0, n_rows, tf + 9);
+  }
+  __syncwarp();
+}
+
+// The same outputs written by the object's own thread, element by element: for the RANSAC solve kernel, whose CTAs must
+// fit beside three crop-kernel CTAs that leave no shared memory for a tile (a tile there cost C3 6 us: the solve CTAs
+// no longer warmed up beside their producer).
+__device__ __forceinline__ void write_pose_direct(const FwdParams& p, int obj, const Fit& f, int status, double n_fit,
+                                                  double ratio, double pass_t, double n_valid, double ctx30) {
   double* po = p.pose + (size_t)obj * POSEFIT_POSE_DOUBLES;
   po[0] = f.s;
 #pragma unroll
@@ -404,7 +490,7 @@ __device__ __forceinline__ void write_pose(const FwdParams& p, int obj, const Fi
   cx[23] = (status == PF_OK) ? n_fit : 0.0;
 #pragma unroll
   for (int i = 0; i < 3; ++i) { cx[24 + i] = f.mux[i]; cx[27 + i] = f.muy[i]; }
-  cx[30] = 0.0;
+  cx[30] = ctx30;
   cx[31] = 0.0;
   p.status[obj] = status;
   p.n_valid[obj] = (int)n_valid;
