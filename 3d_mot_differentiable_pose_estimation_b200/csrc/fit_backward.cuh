@@ -33,7 +33,6 @@ struct BwdParams {
   int vec_ok;
   int early_dep;
   int opc;                // K-backward-coef: objects per CTA (posefit_common.cuh: solve_object)
-  int prefetch;           // K-backward: units per CTA whose crop lines are requested into L2 before griddepcontrol.wait
 };
 
 struct BwdCoef {          // per-object coefficients, already scaled by 1/n
@@ -136,23 +135,6 @@ __global__ void __launch_bounds__(128) fit_backward_coef_kernel(const BwdParams 
   PF_TRACE_END(2);
 }
 
-// While the coefficient kernel runs (a few us in which HBM is idle) a CTA of the streaming kernel already knows which
-// pixels it will read first: threads 0-4 ask L2 for them (three NOC planes, depth, mask of the CTA's first p.prefetch
-// units).  A prefetch moves no data into the SM, so it is safe before griddepcontrol.wait whoever produced the crops.
-// Out of line: its registers must not count against the streaming loop's.
-__device__ __noinline__ void bwd_prefetch(const float* noc, const float* depth, const uint8_t* mask, int n_units,
-                                          int chunks_per_obj, int chunk_px, int P, int count) {
-  for (int r = 0, u = blockIdx.x; r < count && u < n_units; ++r, u += gridDim.x) {
-    const int obj = u / chunks_per_obj;
-    const int px0 = (u - obj * chunks_per_obj) * chunk_px;
-    const int n = min(chunk_px, P - px0);
-    const size_t ob = (size_t)obj * P;
-    if (threadIdx.x < 3) l2_prefetch_bulk(noc + ob * 3 + (size_t)threadIdx.x * P + px0, (uint32_t)n * 4u);
-    else if (threadIdx.x == 3) l2_prefetch_bulk(depth + ob + px0, (uint32_t)n * 4u);
-    else l2_prefetch_bulk(mask + ob + px0, (uint32_t)n);
-  }
-}
-
 struct BwdLoad {
   float4 a0, a1, a2, zz;
   uchar4 mm, im;
@@ -171,8 +153,6 @@ __global__ void __launch_bounds__(NT, MINB) fit_backward_kernel(const BwdParams 
   static_assert(sizeof(BwdCoef) == 144, "coefficient record is 9 x 16 bytes");
   PF_TRACE_BEGIN(3);
 #if __CUDA_ARCH__ >= 900
-  if (p.prefetch > 0 && threadIdx.x < 5)
-    bwd_prefetch(p.noc, p.depth, p.mask, p.B * p.chunks_per_obj, p.chunks_per_obj, p.chunk_px, p.P, p.prefetch);
   if (p.early_dep & 8) asm volatile("griddepcontrol.launch_dependents;");   // the next call's first kernel may queue up
   asm volatile("griddepcontrol.wait;" ::: "memory");            // coefficients written by fit_backward_coef_kernel
   if (!(p.early_dep & 8)) asm volatile("griddepcontrol.launch_dependents;");

@@ -150,13 +150,6 @@ struct ObjGeom {
   bool simple;
 };
 
-// Ask L2 for [ptr, ptr + bytes) (widened to 16-byte granules): one instruction, nothing lands in the SM.
-__device__ __forceinline__ void l2_prefetch_bulk(const void* ptr, uint32_t bytes) {
-  const uint64_t a = reinterpret_cast<uint64_t>(ptr), a0 = a & ~15ull;
-  const uint32_t n = (uint32_t)((a + bytes + 15ull - a0) & ~15ull);
-  if (n != 0u) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a0), "r"(n) : "memory");
-}
-
 __device__ __forceinline__ void cp_async_8(void* dst, const void* src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }

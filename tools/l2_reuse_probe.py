@@ -2,7 +2,11 @@
 """Does the backward pass find the forward pass's crops in L2?  (tooling, like tests/)
 
 Times fit_backward (coefficients + streaming kernel) of a C4-shaped batch right after a forward pass over the SAME
-crops and right after a forward pass over OTHER crops, for several POSEFIT_L2_KEEP_MB settings."""
+crops and right after a forward pass over OTHER crops (eager launches, events between the calls).  Round-2 result
+(profiles/r02_l2_reuse_probe.txt): 2 us apart even when all crops fit in L2 (39 MB) -- the backward kernel of a short
+batch is bound by its per-unit latency chain, not by where its reads come from; an evict-last policy on the forward
+pass's copies and an L2 prefetch ahead of the backward kernel's griddepcontrol.wait were built, measured (no change on
+BASELINE config 4) and removed."""
 import argparse
 import importlib
 import os
@@ -21,7 +25,6 @@ def main():
     ap.add_argument('--size', type=int, default=112)
     ap.add_argument('--sets', type=int, default=8)
     ap.add_argument('--reps', type=int, default=24)
-    ap.add_argument('keep', nargs='*', default=['0', '64', '128'])
     a = ap.parse_args()
     dev = torch.device('cuda')
     kinv = pf.default_kinv(dev)
@@ -30,9 +33,7 @@ def main():
     g = (torch.randn(n, device=dev), torch.randn(n, 9, device=dev), torch.randn(n, 3, device=dev))
     mb = n * sz * sz * 17 / 2**20
     print(f'{n} objects {sz}x{sz}: {mb:.1f} MB of crops per batch, {n * sz * sz * 12 / 2**20:.1f} MB of gradients written')
-    for keep in a.keep:
-        os.environ['POSEFIT_L2_KEEP_MB'] = keep
-        pf._lib.reload_knobs()
+    for keep in ('-',):
         ctxs = []
         for c in sets:
             raw = pf.pose_fit_raw(c['noc'], c['depth'], c['mask'], c['bbox_xy0'], kinv)
@@ -57,7 +58,7 @@ def main():
                     bw.append(e1.elapsed_time(e2) * 1e3)
             fw.sort(); bw.sort()
             res[mode] = (fw[len(fw) // 2], bw[len(bw) // 2])
-        print(f'L2_KEEP_MB={keep:>4s}: backward after a forward over the same crops {res["same"][1]:6.1f} us, over other crops '
+        print(f'backward after a forward over the same crops {res["same"][1]:6.1f} us, over other crops '
               f'{res["other"][1]:6.1f} us   (forward {res["same"][0]:.1f} / {res["other"][0]:.1f} us; eager launches, events '
               f'between the calls)', flush=True)
 
