@@ -46,7 +46,7 @@ class Arena:
 
 @pytest.mark.parametrize('h,w,b,n_hyp', [(64, 64, 37, 128), (3, 5, 4, 0), (17, 16, 9, 12), (20, 20, 300, 16),
                                          (112, 112, 5, 32), (33, 64, 11, 130), (150, 172, 2, 8), (1, 1, 3, 0),
-                                         (64, 64, 4096, 0)])
+                                         (64, 64, 4096, 0), (16, 16, 4737, 8), (16, 16, 149, 8)])
 def test_no_write_outside_outputs(pf, h, w, b, n_hyp):
     lib = pf._lib.lib()
     d = pf.synth.make_objects(b, h, w, seed=5, device='cuda', n_hyp=max(n_hyp, 1), align_x0=1 if w % 4 else 4)

@@ -355,7 +355,9 @@ def test_launch_variants_agree(pf, knob):
                 {'POSEFIT_RANSAC_SCREEN': '0', 'POSEFIT_RANSAC_THREADS': '256', 'POSEFIT_RANSAC_MINB': '3'},
                 {'POSEFIT_RANSAC_SCREEN': '0', 'POSEFIT_NO_IDX_PRELOAD': '1'},
                 {'POSEFIT_RANSAC_SCREEN': '0', 'POSEFIT_NO_EARLY_ISSUE': '1'},
-                {'POSEFIT_PDL_MASK': '15'}, {'POSEFIT_PDL_MASK': '5'}, {'POSEFIT_BWD_MINB': '3'}, {'POSEFIT_BWD_MINB': '4'}]
+                {'POSEFIT_PDL_MASK': '15'}, {'POSEFIT_PDL_MASK': '5'}, {'POSEFIT_BWD_MINB': '3'}, {'POSEFIT_BWD_MINB': '4'},
+                {'POSEFIT_SOLVE_SPREAD': '0'}, {'POSEFIT_SOLVE_SPREAD': '0', 'POSEFIT_PREWARM': '1'},
+                {'POSEFIT_BWD_CTAS_PER_SM': '12'}, {'POSEFIT_BWD_CTAS_PER_SM': '1'}]
     for env in variants:
         for k, v in env.items():
             knob.set(k, v)
@@ -367,6 +369,42 @@ def test_launch_variants_agree(pf, knob):
         assert float((plain.pose[:, :13] - base[0].pose[:, :13]).abs().max()) < 1e-10, env
         assert float((rans.pose[:, :13] - base[1].pose[:, :13]).abs().max()) < 1e-10, env
         assert float((gn - base[2]).abs().max()) <= 1e-5 * float(base[2].abs().max()), env
+
+
+@pytest.mark.parametrize('n_obj', [1, 31, 33, 147, 149, 297, 4737, 4800, 9473, 19000])
+def test_solve_kernels_spread_over_sms_agree(pf, knob, n_obj):
+    """The one-thread-per-object kernels put ceil(B / SMs) objects in a CTA and move their records through per-warp
+    shared-memory tiles (posefit_common.cuh: solve_object, write_pose).  Batch sizes around every boundary of that mapping --
+    one object per CTA, a partly filled warp, a second warp with one lane, full 128-thread CTAs -- must give exactly what
+    one full CTA per 128 objects gives (POSEFIT_SOLVE_SPREAD=0: same moments, same arithmetic, so bit-identical records)
+    for the plain fit, the RANSAC fit and the backward pass, and what the element-wise stores of the warm-up policy give
+    (POSEFIT_PREWARM=1, RANSAC fit; the plain path streams with another plan there, so only rounding-equal)."""
+    h = w = 16
+    d = pf.synth.make_objects(n_obj, h, w, seed=100 + n_obj, n_hyp=8)
+    t = _cuda(d)
+    g = (torch.randn(n_obj, device='cuda'), torch.randn(n_obj, 9, device='cuda'), torch.randn(n_obj, 3, device='cuda'))
+
+    def run():
+        plain = pf.pose_fit_raw(t['noc'], t['depth'], t['mask'], t['bbox_xy0'])
+        rans = pf.pose_fit_raw(t['noc'], t['depth'], t['mask'], t['bbox_xy0'], sample_idx=t['sample_idx'])
+        gn, _ = pf.pose_fit_backward_raw(t['noc'], t['depth'], t['mask'], None, t['bbox_xy0'], None, plain.ctx,
+                                         plain.status, *g)
+        torch.cuda.synchronize()
+        return plain, rans, gn
+    new = run()
+    knob.set('POSEFIT_SOLVE_SPREAD', '0')
+    old = run()
+    knob.set('POSEFIT_PREWARM', '1')
+    direct = run()
+    knob.clear('POSEFIT_SOLVE_SPREAD')
+    knob.clear('POSEFIT_PREWARM')
+    assert float((new[0].pose[:, :13] - direct[0].pose[:, :13]).abs().max()) < 1e-10
+    for a, b in ((new[0], old[0]), (new[1], old[1]), (new[1], direct[1])):
+        for f in ('pose', 'ctx', 'status', 'n_valid'):
+            assert torch.equal(getattr(a, f), getattr(b, f)), f
+    assert torch.equal(new[1].inlier_mask, old[1].inlier_mask) and torch.equal(new[1].winner, old[1].winner)
+    assert torch.equal(new[2], old[2])
+    assert int((new[0].status == 0).sum()) >= n_obj * 9 // 10            # (not vacuous: the objects were fitted)
 
 
 def test_ransac_fast_and_generic_passes_agree(pf, knob):
