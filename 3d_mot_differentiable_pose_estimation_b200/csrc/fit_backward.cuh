@@ -33,6 +33,7 @@ struct BwdParams {
   int vec_ok;
   int early_dep;
   int opc;                // K-backward-coef: objects per CTA (posefit_common.cuh: solve_object)
+  unsigned int* dyn_counter;   // long launches: ticket counter of K-backward's units (zeroed by K-backward-coef), else NULL
 };
 
 struct BwdCoef {          // per-object coefficients, already scaled by 1/n
@@ -127,6 +128,7 @@ __global__ void __launch_bounds__(128) fit_backward_coef_kernel(const BwdParams 
   if (!(p.early_dep & 4)) asm volatile("griddepcontrol.launch_dependents;");
 #endif
   PF_TRACE_BEGIN(10);
+  if (p.dyn_counter != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *p.dyn_counter = 0u;   // K-backward's tickets
   const int o = solve_object(p.opc, p.B);
   if (o >= p.B) return;
   BwdCoef c;
@@ -147,11 +149,12 @@ struct BwdLoad {
 // (Computing the record inside this kernel instead of fit_backward_coef_kernel -- one thread per CTA, behind the
 // streaming of the previous unit -- was built and measured on BASELINE config 4: 64.7 us against 64.9 us, i.e. the
 // separate kernel already hides behind the programmatic dependent launch; not kept.)
-template <int NT, int MINB>
+template <int NT, int MINB, bool DYN = false>
 __global__ void __launch_bounds__(NT, MINB) fit_backward_kernel(const BwdParams p) {
   __shared__ __align__(16) BwdCoef coefs[2];
   static_assert(sizeof(BwdCoef) == 144, "coefficient record is 9 x 16 bytes");
   PF_TRACE_BEGIN(3);
+  PF_TRACE_END(6);                                              // (latest first instruction)
 #if __CUDA_ARCH__ >= 900
   if (p.early_dep & 8) asm volatile("griddepcontrol.launch_dependents;");   // the next call's first kernel may queue up
   asm volatile("griddepcontrol.wait;" ::: "memory");            // coefficients written by fit_backward_coef_kernel
@@ -175,9 +178,17 @@ __global__ void __launch_bounds__(NT, MINB) fit_backward_kernel(const BwdParams 
     d.im = make_uchar4(1, 1, 1, 1);
     if (p.inlier_mask) d.im = __ldcs(reinterpret_cast<const uchar4*>(p.inlier_mask + ob + i));
   };
+  // Which unit comes next: blockIdx + k * gridDim (short launches), or -- long launches, where SMs that stream more slowly
+  // than others would otherwise set the kernel's time -- the first two of them and then tickets from p.dyn_counter.
+  // Thread 0 draws the ticket of iteration k + 2 at the top of iteration k and publishes it at the bottom (the value is
+  // back by then); the barrier at the top of iteration k + 1 makes it visible, one iteration before the unit is needed
+  // (its coefficient record is requested a unit ahead).
+  __shared__ int tickets[2];
+  constexpr bool dyn = DYN;                          // (its own instantiation: the short-launch kernel keeps its registers)
   provide((int)blockIdx.x, 0);
   int k = 0;
-  for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++k) {
+  int nxt = (int)blockIdx.x + (int)gridDim.x;
+  for (int unit = blockIdx.x; unit < n_units; unit = nxt, ++k) {
     const int obj = unit / p.chunks_per_obj;
     const int ch = unit - obj * p.chunks_per_obj;
     const int px0 = ch * p.chunk_px;
@@ -190,7 +201,11 @@ __global__ void __launch_bounds__(NT, MINB) fit_backward_kernel(const BwdParams 
     float* g2p = g1p + p.P;
     cp_async_wait_all();
     __syncthreads();                                   // this unit's record is visible; the other buffer is free
-    provide(unit + (int)gridDim.x, (k + 1) & 1);
+    if (dyn) { if (k > 0) nxt = tickets[(k - 1) & 1]; }
+    else nxt = unit + (int)gridDim.x;
+    provide(nxt, (k + 1) & 1);
+    unsigned int drawn = 0u;
+    if (dyn && tid == 0) drawn = atomicAdd(p.dyn_counter, 1u);
     const BwdCoef c = coefs[k & 1];
     if (p.vec_ok) {
       auto emit = [&](int ii, const BwdLoad& d) {
@@ -245,8 +260,10 @@ __global__ void __launch_bounds__(NT, MINB) fit_backward_kernel(const BwdParams 
         if (p.grad_depth) p.grad_depth[ob + ii] = oz;
       }
     }
+    if (dyn && tid == 0) tickets[k & 1] = 2 * (int)gridDim.x + (int)drawn;   // the unit of iteration k + 2
   }
   PF_TRACE_END(3);
+  PF_TRACE_BEGIN(7);                                            // (earliest warp done)
 }
 
 }  // namespace posefit

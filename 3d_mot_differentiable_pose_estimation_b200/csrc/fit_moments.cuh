@@ -153,9 +153,17 @@ struct LaneSums {
 // one set of request / object / ring bookkeeping per 256 pixels, the second chunk addressed by immediate
 // offsets.  The per-chunk overhead (a third of the loop's instructions) is what makes this kernel issue-limited
 // when the board's power cap lowers the SM clock.
-template <bool POINTS, int DEPTH, int VEC, bool PAIR = false>
+// DYN (long batches of full chunks, at least DEPTH chunks per object): a warp takes WHOLE objects -- object gw first, the
+// following ones from a ticket counter in the workspace (zeroed by the host before the launch) -- instead of a fixed
+// range of the chunk stream.  SMs do not stream at the same rate (tools/trace_step.py: on the 125 000-object shard the
+// last warps of some TPCs finish 60 us after most others), and with equal ranges the slowest SM sets the kernel's time.
+// The request stream draws the next ticket when it enters an object, a whole object ahead of its use; the consumer
+// follows it (it is less than one object behind).  Every object is summed by ONE warp in a fixed lane / chunk order,
+// whichever warp that is: results do not depend on the assignment.
+template <bool POINTS, int DEPTH, int VEC, bool PAIR = false, bool DYN = false>
 __global__ void __launch_bounds__(512, 1) fit_moments_kernel(const FwdParams p) {
   static_assert(!PAIR || (!POINTS && VEC == 2 && DEPTH % 2 == 0 && DEPTH >= 4), "PAIR: full aligned chunks, even ring");
+  static_assert(!DYN || (!POINTS && VEC == 2 && !PAIR), "DYN: full aligned chunks, one chunk per iteration");
   extern __shared__ __align__(128) unsigned char smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   unsigned char* ring = smem + (size_t)warp * p.warp_smem_bytes;               // DEPTH stages of kChunkBytes
@@ -167,19 +175,22 @@ __global__ void __launch_bounds__(512, 1) fit_moments_kernel(const FwdParams p) 
   // has completed.  Every kernel of the chain touches global memory only after its own wait, so
   // completion order (every RAW / WAR dependence between consecutive kernels) is unchanged.
   PF_TRACE_BEGIN(0);
+  PF_TRACE_END(4);                                            // (latest first instruction: the launch stagger)
   if (p.early_dep & 1) asm volatile("griddepcontrol.launch_dependents;");
   asm volatile("griddepcontrol.wait;" ::: "memory");          // inputs may come from the previous kernel in the stream
   if (!(p.early_dep & 1)) asm volatile("griddepcontrol.launch_dependents;");
   PF_TRACE_BEGIN(8);
 #endif
   const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
-  const long long c_begin = gw * p.chunks_per_warp;
+  const long long c_begin = DYN ? gw * p.chunks_per_obj : gw * p.chunks_per_warp;
   if (c_begin >= p.total_chunks) return;
   const int n_chunks = (int)min((long long)p.chunks_per_warp, p.total_chunks - c_begin);
 
   const int cpo = p.chunks_per_obj;
   int obj = (int)(c_begin / cpo);
   int ch = (int)(c_begin - (long long)obj * cpo);
+  int ticket = 0;                                             // DYN, lane 0: the object after the one being requested
+  if (DYN && lane == 0) ticket = p.dyn_base + (int)atomicAdd(p.dyn_counter, 1u);
   LaneSums acc;
   acc.clear();
   ObjGeom g = {};
@@ -194,7 +205,7 @@ __global__ void __launch_bounds__(512, 1) fit_moments_kernel(const FwdParams p) 
     acc.finish(POINTS ? 0.0 : 0.5, !POINTS, out);
     if (lane == 0) {
       const long long first = ((long long)o * cpo) / p.chunks_per_warp;     // first warp that touches object o
-      double* w = p.ws + ((size_t)o * p.max_parts + (size_t)(gw - first)) * kAccPlain;
+      double* w = p.ws + ((size_t)o * p.max_parts + (DYN ? (size_t)0 : (size_t)(gw - first))) * kAccPlain;
 #pragma unroll
       for (int i = 0; i < kAccPlain; ++i) w[i] = out[i];
     }
@@ -210,13 +221,19 @@ __global__ void __launch_bounds__(512, 1) fit_moments_kernel(const FwdParams p) 
   const float* q_dz = p.depth + (size_t)obj * P + q_px;
   const uint8_t* q_mk = p.mask + (size_t)obj * P + q_px;
   auto request_next = [&]() {
-    if (q_left > 0) {
+    if (DYN ? q_obj < p.B : q_left > 0) {
       request_chunk<VEC>(ring + q_slot * kChunkBytes, ring_s + q_slot * kChunkBytes, q_n0, q_dz, q_mk, P, q_px, lane);
       --q_left;
       if (++q_slot == DEPTH) q_slot = 0;
       if (++q_ch == cpo) {
         q_ch = 0;
-        ++q_obj;
+        if (DYN) {
+          q_obj = __shfl_sync(0xffffffffu, ticket, 0);        // drawn when the stream entered the object it now leaves
+          if (lane == 0 && q_obj < p.B) ticket = p.dyn_base + (int)atomicAdd(p.dyn_counter, 1u);
+          if (q_obj > p.B) q_obj = p.B;                       // (pointer arithmetic below stays inside one object past the end)
+        } else {
+          ++q_obj;
+        }
         q_px = 4 * lane;
         q_n0 = p.noc + (size_t)q_obj * 3 * P + q_px;
         q_dz = p.depth + (size_t)q_obj * P + q_px;
@@ -354,6 +371,8 @@ __global__ void __launch_bounds__(512, 1) fit_moments_kernel(const FwdParams p) 
     }
     write_part(cur_obj);
     PF_TRACE_END(0);
+    PF_TRACE_BEGIN(5);                                        // (earliest warp done)
+    PF_TRACE_WARP_END();
     return;
   }
   if (!POINTS) {
@@ -361,7 +380,7 @@ __global__ void __launch_bounds__(512, 1) fit_moments_kernel(const FwdParams p) 
     for (int i = 0; i < DEPTH - 1; ++i) request_next();
   }
 
-  for (int it = 0; it < n_chunks; ++it) {
+  for (int it = 0; DYN ? obj < p.B : it < n_chunks; ++it) {
     if (!POINTS) request_next();                              // refill the stage consumed last iteration
 
     if (obj != cur_obj) {
@@ -473,11 +492,18 @@ __global__ void __launch_bounds__(512, 1) fit_moments_kernel(const FwdParams p) 
       if (col >= p.W) { col -= p.W; ++row; }
     }
     px0 += kChunkPx;
-    if (++ch == cpo) { ch = 0; ++obj; px0 = 4 * lane; }
+    if (++ch == cpo) {
+      ch = 0;
+      px0 = 4 * lane;
+      if (DYN) obj = q_obj;                                   // the request stream is inside this warp's next object
+      else ++obj;
+    }
     if (++slot == DEPTH) slot = 0;
   }
   write_part(cur_obj);
   PF_TRACE_END(0);
+  PF_TRACE_BEGIN(5);
+  PF_TRACE_WARP_END();
 }
 
 // One thread per object: merge the partial moments and solve (pose_utils.py:16-61).

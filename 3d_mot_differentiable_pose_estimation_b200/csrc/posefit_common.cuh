@@ -103,6 +103,8 @@ struct FwdParams {
   int n_stages, tma_ok;
   int early_dep;                // bit k: kernel k of the chain signals its dependents before its own wait
   int prewarm;                  // K-solve kernels: run a warm-up pass before griddepcontrol.wait (small grids)
+  unsigned int* dyn_counter;    // K-moments, DYN instantiation: ticket counter (workspace, zeroed before the launch)
+  int dyn_base;                 //   first ticket = number of warps in the grid (warp gw starts with object gw)
   int opc;                      // K-solve kernels: objects per CTA (threads beyond it idle; see solve_object)
   int n_words;                  // ceil(P / 32)
   uint32_t w_magic;             // ceil(2^32 / W): px / W == __umulhi(px, w_magic) for px, W < 65536
@@ -374,9 +376,11 @@ __device__ __forceinline__ void block_reduce(double (&v)[N], double* red, double
 // Debug build only (make trace): wall-clock span of every kernel of the plain path -- earliest start and latest end over
 // its warps (%globaltimer, ns) -- read back through posefit_debug_trace (tools/trace_step.py).
 // ids: 0 moments, 1 solve, 2 backward coefficients, 3 backward; 8 + id = the same kernel after its griddepcontrol.wait;
-// 12 / 13 = solve kernel: moments merged / solved.
+// 12 / 13 = solve kernel: moments merged / solved; 4 / 6 = latest first instruction of moments / backward (slot [2k+1]),
+// 5 / 7 = their earliest finished warp (slot [2k]).
 #ifdef PF_TRACE
 __device__ unsigned long long g_trace[32];
+__device__ unsigned long long g_trace_warp[4096];          // moments kernel: when each warp (CTA * 16 + warp) finished
 __device__ __forceinline__ unsigned long long pf_now() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -385,7 +389,9 @@ __device__ __forceinline__ unsigned long long pf_now() {
 #define PF_TRACE_BEGIN(k) do { if ((threadIdx.x & 31) == 0) atomicMin(&g_trace[2 * (k)], pf_now()); } while (0)
 #define PF_TRACE_END(k) do { if ((threadIdx.x & 31) == 0) atomicMax(&g_trace[2 * (k) + 1], pf_now()); } while (0)
 #define PF_TRACE_BOTH(k) do { PF_TRACE_BEGIN(k); PF_TRACE_END(k); } while (0)   /* earliest and latest warp at a point */
+#define PF_TRACE_WARP_END() do { if ((threadIdx.x & 31) == 0) g_trace_warp[(blockIdx.x * 16 + (threadIdx.x >> 5)) & 4095] = pf_now(); } while (0)
 #else
+#define PF_TRACE_WARP_END() do { } while (0)
 #define PF_TRACE_BEGIN(k) do { } while (0)
 #define PF_TRACE_END(k) do { } while (0)
 #define PF_TRACE_BOTH(k) do { } while (0)

@@ -407,6 +407,59 @@ def test_solve_kernels_spread_over_sms_agree(pf, knob, n_obj):
     assert int((new[0].status == 0).sum()) >= n_obj * 9 // 10            # (not vacuous: the objects were fitted)
 
 
+def test_ticketed_long_batch_agrees_with_fixed_ranges(pf, knob):
+    """Long batches hand whole objects to the warps of fit_moments_kernel through a ticket counter (the DYN instantiation)
+    instead of fixed ranges of the chunk stream.  Same pixels, same per-lane order, one warp per object instead of up to
+    two: statuses and counts identical, poses to rounding -- and identical from run to run, whichever warp drew which
+    object.  Checked against the fixed-range kernel (POSEFIT_DYNAMIC=0) and, for a sample of objects, the oracle."""
+    n_obj, h, w = 19000, 32, 32
+    d = pf.synth.make_objects(n_obj, h, w, seed=77)
+    t = _cuda(d)
+    a = pf.pose_fit_raw(t['noc'], t['depth'], t['mask'], t['bbox_xy0'])
+    b = pf.pose_fit_raw(t['noc'], t['depth'], t['mask'], t['bbox_xy0'])
+    knob.set('POSEFIT_DYNAMIC', '0')
+    c = pf.pose_fit_raw(t['noc'], t['depth'], t['mask'], t['bbox_xy0'])
+    knob.clear('POSEFIT_DYNAMIC')
+    torch.cuda.synchronize()
+    assert torch.equal(a.pose, b.pose) and torch.equal(a.ctx, b.ctx)                  # reproducible
+    assert torch.equal(a.status, c.status) and torch.equal(a.n_valid, c.n_valid)
+    assert int((a.status == 0).sum()) >= n_obj * 9 // 10
+    assert float((a.pose[:, :13] - c.pose[:, :13]).abs().max()) < 1e-10
+    sel = torch.tensor([0, 1, 2367, 2368, 2369, 9999, n_obj - 2, n_obj - 1])          # first tickets, a middle one, the last
+    ora = po.batch_pose(d['noc'][sel].numpy(), d['depth'][sel].numpy(), d['mask'][sel].numpy(), d['bbox_xy0'][sel].numpy())
+    pose = a.pose[sel.cuda()].cpu().numpy()
+    for i, o in enumerate(ora):
+        assert int(a.status[sel[i]]) == o['status'] and int(a.n_valid[sel[i]]) == o['n_valid']
+        if o['status'] == 0:
+            assert rot_err_deg(pose[i, 1:10].reshape(3, 3), o['R']) <= ROT_TOL_DEG
+            assert abs(pose[i, 0] - o['s']) <= REL_TOL * abs(o['s'])
+            assert np.linalg.norm(pose[i, 10:13] - o['t']) <= REL_TOL * np.linalg.norm(o['t'])
+
+
+def test_ticketed_backward_is_bit_identical(pf, knob):
+    """Long backward launches hand their (object, chunk) units out through a ticket counter that the coefficient kernel
+    zeroes (fit_backward.cuh).  Every pixel's gradient is computed by whichever CTA draws its unit, from the same record:
+    bit-identical to the strided assignment (POSEFIT_DYNAMIC=0), every unit written exactly once."""
+    n_obj, h, w = 38000, 48, 48                                   # 2 units per object: 76 000 units
+    t = pf.synth.make_objects(n_obj, h, w, seed=78, device='cuda')
+    g = (torch.randn(n_obj, device='cuda'), torch.randn(n_obj, 9, device='cuda'), torch.randn(n_obj, 3, device='cuda'))
+    fwd = pf.pose_fit_raw(t['noc'], t['depth'], t['mask'], t['bbox_xy0'])
+
+    def bwd():
+        gn, gd = pf.pose_fit_backward_raw(t['noc'], t['depth'], t['mask'], None, t['bbox_xy0'], None, fwd.ctx, fwd.status, *g,
+                                          want_depth_grad=True)
+        torch.cuda.synchronize()
+        return gn, gd
+    a = bwd()
+    b = bwd()
+    knob.set('POSEFIT_DYNAMIC', '0')
+    c = bwd()
+    knob.clear('POSEFIT_DYNAMIC')
+    assert torch.equal(a[0], b[0]) and torch.equal(a[0], c[0])
+    assert torch.equal(a[1], c[1])
+    assert float(a[0].abs().max()) > 0.0
+
+
 def test_ransac_fast_and_generic_passes_agree(pf, knob):
     d = pf.synth.make_objects(64, 64, 64, seed=22, n_hyp=128)
     t = _cuda(d)

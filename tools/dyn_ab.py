@@ -1,0 +1,50 @@
+#!/usr/bin/env python
+"""A/B of the ticketed (POSEFIT_DYNAMIC=1) and the fixed assignment of work on the config-5 shard, alternating in one process
+(tooling, like tests/).  Prints forward / backward interval per variant, median over --steps steps per round."""
+import argparse
+import importlib
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+pf = importlib.import_module('3d_mot_differentiable_pose_estimation_b200')
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--objects', type=int, default=125000)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--rounds', type=int, default=4)
+    a = ap.parse_args()
+    dev = torch.device('cuda')
+    kinv = pf.default_kinv(dev)
+    n = a.objects
+    c = pf.synth.make_objects(n, 64, 64, seed=5000, device=dev)
+    g = (torch.randn(n, device=dev), torch.randn(n, 9, device=dev), torch.randn(n, 3, device=dev))
+    gn = torch.empty_like(c['noc'])
+    for rnd in range(a.rounds):
+        for dyn in ('1', '0'):
+            os.environ['POSEFIT_DYNAMIC'] = dyn
+            pf._lib.reload_knobs()
+            fw, bw = [], []
+            for s in range(a.steps + 3):
+                e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+                e0.record()
+                raw = pf.pose_fit_raw(c['noc'], c['depth'], c['mask'], c['bbox_xy0'], kinv)
+                e1.record()
+                pf.pose_fit_backward_raw(c['noc'], c['depth'], c['mask'], None, c['bbox_xy0'], kinv, raw.ctx, raw.status, *g, out=gn)
+                e2.record()
+                torch.cuda.synchronize()
+                if s >= 3:
+                    fw.append(e0.elapsed_time(e1))
+                    bw.append(e1.elapsed_time(e2))
+            fw.sort(); bw.sort()
+            print(f'round {rnd} DYNAMIC={dyn}: forward {fw[len(fw) // 2]:.4f} ms, backward {bw[len(bw) // 2]:.4f} ms, '
+                  f'step {fw[len(fw) // 2] + bw[len(bw) // 2]:.4f} ms', flush=True)
+
+
+if __name__ == '__main__':
+    main()

@@ -77,9 +77,12 @@ def main():
         torch.cuda.synchronize()
         lib.posefit_debug_trace(buf, 0)
         t = list(buf)
-        rows.append((a0.elapsed_time(a1) * 1e3, t))
+        wbuf = (ctypes.c_ulonglong * 4096)()
+        if hasattr(lib, 'posefit_debug_trace_warps'):
+            lib.posefit_debug_trace_warps(wbuf)
+        rows.append((a0.elapsed_time(a1) * 1e3, t, list(wbuf)))
     rows.sort(key=lambda r: r[0])
-    us, t = rows[len(rows) // 2]                                 # the median replay
+    us, t, wt = rows[len(rows) // 2]                             # the median replay
     t0 = t[0]
     print(f'{n} objects {sz}x{sz}, one replay on an idle GPU: {us:.1f} us between the events around it; stamps relative '
           f'to the first instruction of the streaming forward kernel')
@@ -88,10 +91,30 @@ def main():
             continue
         print(f'{NAMES[k]:13s} first instruction {(t[2 * k] - t0) / 1e3:7.2f}  past its wait {(t[2 * (8 + k)] - t0) / 1e3:7.2f}  '
               f'last warp done {(t[2 * k + 1] - t0) / 1e3:7.2f} us')
+        if k == 0:
+            warp_report(wt, t0)
+        if k in (0, 3):                                          # streaming kernels: how far apart their warps start / end
+            a_, b_ = (4, 5) if k == 0 else (6, 7)
+            print(f'    latest first instruction {(t[2 * a_ + 1] - t0) / 1e3:7.2f}, earliest warp done {(t[2 * b_] - t0) / 1e3:7.2f} us')
         if k == 1:
             def span(i):
                 return f'{(t[2 * i] - t0) / 1e3:.2f} .. {(t[2 * i + 1] - t0) / 1e3:.2f}'
             print(f'    solve, earliest .. latest warp: past the wait {span(9)}, moments merged {span(12)}, solved {span(13)} us')
+
+
+def warp_report(wt, t0):
+    """moments kernel: when the warps of every CTA finished (g_trace_warp) -- spread inside a CTA vs between CTAs"""
+    import numpy as np
+    w = (np.array(wt, dtype=np.float64).reshape(256, 16) - t0) / 1e3
+    live = w[(w > 0).all(axis=1) & (w < 1e6).all(axis=1)]
+    if len(live) == 0:
+        return
+    print(f'    warps finished (us after the first instruction), {len(live)} CTAs x 16 warps: all {live.min():.1f} .. {live.max():.1f}; '
+          f'per CTA first {live.min(axis=1).mean():.1f} / last {live.max(axis=1).mean():.1f} on average; CTA means '
+          f'{live.mean(axis=1).min():.1f} .. {live.mean(axis=1).max():.1f}')
+    print('    by warp index (mean over CTAs): ' + ' '.join(f'{x:.1f}' for x in live.mean(axis=0)))
+    if os.environ.get('TRACE_PER_CTA'):
+        print('    last warp of every CTA, in blockIdx order: ' + ' '.join(f'{x:.0f}' for x in live.max(axis=1)))
 
 
 if __name__ == '__main__':
