@@ -508,14 +508,15 @@ __global__ void __launch_bounds__(512, 1) fit_moments_kernel(const FwdParams p) 
 
 // One thread per object: merge the partial moments and solve (pose_utils.py:16-61).
 //
-// This kernel is pure latency: ~3 k dependent instructions executed once per thread, instruction
-// cache cold.  Two things take that latency off the critical path of a small batch:
-//  * warm-up pass (p.prewarm, set when the whole grid is resident in one wave): the CTAs are
-//    scheduled while K-moments still runs (programmatic dependent launch) and walk through the very
-//    same solve code on synthetic moments BEFORE griddepcontrol.wait, so the instruction fetches
-//    overlap the streaming kernel; the real pass then runs out of a warm instruction cache;
-//  * the partial records of an object are read four at a time (68 independent loads in flight)
-//    instead of one record per round trip, in the same summation order.
+// This kernel is pure latency: ~3 k dependent instructions executed once per thread.  What keeps it short:
+//  * short batches put ceil(B / SMs) objects in a CTA (solve_object): the element-wise loads of the partial records
+//    touch one line per lane, which an SM's load / store unit takes one at a time, so every SM takes a share;
+//  * the partial records of an object are read four at a time (68 independent loads in flight) instead of one record
+//    per round trip, in the same summation order;
+//  * the pose / ctx records leave through a per-warp shared-memory tile, with consecutive addresses (write_pose);
+//  * optional warm-up pass (p.prewarm, POSEFIT_PREWARM=1; the default of round 1, off now): the CTAs are scheduled while
+//    K-moments still runs (programmatic dependent launch) and walk through the same solve code on synthetic moments
+//    BEFORE griddepcontrol.wait, so that the real pass runs out of a warm instruction cache.
 __global__ void __launch_bounds__(128) fit_solve_kernel(const FwdParams p) {
 #if __CUDA_ARCH__ >= 900
   if (p.early_dep & 2) asm volatile("griddepcontrol.launch_dependents;");
