@@ -69,7 +69,9 @@ int posefit_version(void);
 const char* posefit_error_string(int code);
 
 /* Bytes of device scratch the forward entries need for these sizes (n_hyp = 0 for the
- * plain fit).  May be 0. */
+ * plain fit).  May be 0.  The scratch needs no initialisation and carries nothing from call to call
+ * (partial moments, per-object records and -- long batches -- a ticket counter that the entry itself
+ * zeroes); two calls in flight at the same time need two workspaces. */
 size_t posefit_workspace_bytes(int n_objects, int height, int width, int n_hyp, int n_samp);
 
 /* Plain fit on all valid correspondences of every object.
