@@ -925,3 +925,53 @@ def test_general_and_per_object_intrinsics(pf):
         want[:, rows - y0, cols - x0] = gx.numpy().T
         err = np.abs(noc.grad[i].cpu().numpy() - want).max() / np.abs(want).max()
         assert err <= GRAD_TOL, (i, err)
+
+
+def test_ticketed_long_batch_in_a_graph_and_on_two_streams(pf):
+    """The ticketed kernels keep their counters in the call's own workspace (zeroed by a memset node / by the coefficient
+    kernel): a long forward + backward step can be captured and replayed, and two of them can run side by side on two
+    streams without sharing anything."""
+    n_obj, h, w = 38000, 48, 48
+    d = pf.synth.make_objects(n_obj, h, w, seed=79, device='cuda')
+    d2 = pf.synth.make_objects(n_obj, h, w, seed=80, device='cuda')
+    kinv = pf.default_kinv('cuda')
+    g = (torch.randn(n_obj, device='cuda'), torch.randn(n_obj, 9, device='cuda'), torch.randn(n_obj, 3, device='cuda'))
+
+    def work(c):
+        raw = pf.pose_fit_raw(c['noc'], c['depth'], c['mask'], c['bbox_xy0'], kinv)
+        gn, _ = pf.pose_fit_backward_raw(c['noc'], c['depth'], c['mask'], None, c['bbox_xy0'], kinv, raw.ctx, raw.status, *g)
+        return raw.pose, gn
+
+    eager = [t.clone() for t in work(d)]
+    eager2 = [t.clone() for t in work(d2)]
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        work(d)
+        side.synchronize()
+        with torch.cuda.graph(graph, stream=side):
+            captured = work(d)
+    torch.cuda.current_stream().wait_stream(side)
+    for rep in range(3):
+        for t in captured:
+            t.zero_()
+        graph.replay()
+        torch.cuda.synchronize()
+        for a, b in zip(eager, captured):
+            assert torch.equal(a, b), rep
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    s1.wait_stream(torch.cuda.current_stream())
+    s2.wait_stream(torch.cuda.current_stream())
+    outs = []
+    for _ in range(3):
+        with torch.cuda.stream(s1):
+            o1 = work(d)
+        with torch.cuda.stream(s2):
+            o2 = work(d2)
+        outs.append((o1, o2))
+    torch.cuda.synchronize()
+    for o1, o2 in outs:
+        assert torch.equal(o1[0], eager[0]) and torch.equal(o1[1], eager[1])
+        assert torch.equal(o2[0], eager2[0]) and torch.equal(o2[1], eager2[1])
