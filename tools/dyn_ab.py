@@ -1,6 +1,8 @@
 #!/usr/bin/env python
-"""A/B of the ticketed (POSEFIT_DYNAMIC=1) and the fixed assignment of work on the config-5 shard, alternating in one process
-(tooling, like tests/).  Prints forward / backward interval per variant, median over --steps steps per round."""
+"""A/B of launch knobs on the config-5 shard, alternating the variants in one process (tooling, like tests/).  Default: the
+ticketed (POSEFIT_DYNAMIC=1) against the fixed assignment of work.  A variant is a comma-separated list of POSEFIT_*
+assignments without the prefix (`DYNAMIC=0`, `BWD_CTAS_PER_SM=3,BWD_MINB=3`); `base` = the defaults.  Prints the forward /
+backward interval per variant, median over --steps steps per round."""
 import argparse
 import importlib
 import os
@@ -18,6 +20,7 @@ def main():
     ap.add_argument('--objects', type=int, default=125000)
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--rounds', type=int, default=4)
+    ap.add_argument('variants', nargs='*', default=['DYNAMIC=1', 'DYNAMIC=0'])
     a = ap.parse_args()
     dev = torch.device('cuda')
     kinv = pf.default_kinv(dev)
@@ -26,8 +29,13 @@ def main():
     g = (torch.randn(n, device=dev), torch.randn(n, 9, device=dev), torch.randn(n, 3, device=dev))
     gn = torch.empty_like(c['noc'])
     for rnd in range(a.rounds):
-        for dyn in ('1', '0'):
-            os.environ['POSEFIT_DYNAMIC'] = dyn
+        for var in a.variants:
+            for k in [k for k in os.environ if k.startswith('POSEFIT_') and k != 'POSEFIT_LIB']:
+                del os.environ[k]
+            if var != 'base':
+                for kv in var.split(','):
+                    k, v = kv.split('=')
+                    os.environ['POSEFIT_' + k] = v
             pf._lib.reload_knobs()
             fw, bw = [], []
             for s in range(a.steps + 3):
@@ -42,7 +50,7 @@ def main():
                     fw.append(e0.elapsed_time(e1))
                     bw.append(e1.elapsed_time(e2))
             fw.sort(); bw.sort()
-            print(f'round {rnd} DYNAMIC={dyn}: forward {fw[len(fw) // 2]:.4f} ms, backward {bw[len(bw) // 2]:.4f} ms, '
+            print(f'round {rnd} {var:28s}: forward {fw[len(fw) // 2]:.4f} ms, backward {bw[len(bw) // 2]:.4f} ms, '
                   f'step {fw[len(fw) // 2] + bw[len(bw) // 2]:.4f} ms', flush=True)
 
 
