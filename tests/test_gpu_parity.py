@@ -357,7 +357,8 @@ def test_launch_variants_agree(pf, knob):
                 {'POSEFIT_RANSAC_SCREEN': '0', 'POSEFIT_NO_EARLY_ISSUE': '1'},
                 {'POSEFIT_PDL_MASK': '15'}, {'POSEFIT_PDL_MASK': '5'}, {'POSEFIT_BWD_MINB': '3'}, {'POSEFIT_BWD_MINB': '4'},
                 {'POSEFIT_SOLVE_SPREAD': '0'}, {'POSEFIT_SOLVE_SPREAD': '0', 'POSEFIT_PREWARM': '1'},
-                {'POSEFIT_BWD_CTAS_PER_SM': '12'}, {'POSEFIT_BWD_CTAS_PER_SM': '1'}]
+                {'POSEFIT_BWD_CTAS_PER_SM': '12'}, {'POSEFIT_BWD_CTAS_PER_SM': '1'}, {'POSEFIT_BWD_THREADS': '256'},
+                {'POSEFIT_BWD_THREADS': '128'}]
     for env in variants:
         for k, v in env.items():
             knob.set(k, v)
